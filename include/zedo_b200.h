@@ -1,0 +1,167 @@
+/* zedo_b200.h -- C ABI of the B200-native ZeDO per-pose optimisation loop.
+ *
+ * Drop-in boundary for the hot path of ipl-uw/ZeDO-Release.  The
+ * reference is pure Python over PyTorch, so its "FFI" is a ctypes binding: every entry
+ * point below replaces one reference function (cited as file:line relative to the
+ * reference root) and is what the reference-side stub in INTEGRATION.md binds.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types in any signature.
+ *   - All array pointers are DEVICE pointers to contiguous float32 data in the reference's
+ *     own layouts unless a parameter is marked "host".
+ *   - All work is enqueued on the caller's stream (cudaStream_t passed as void*; NULL =
+ *     legacy default stream); no hidden synchronisation except where noted.
+ *   - Return value: 0 = OK, <0 = ZEDO_E_* argument error, >0 = cudaError_t.  Never throws.
+ *   - A plan is bound to one device and one stream at a time and is not thread-safe
+ *     (one plan per process/GPU, matching one-process-per-GPU sharding).
+ *   - There is no CPU fallback: every compute entry point fails with a CUDA error when no
+ *     sm_100 device is present.
+ */
+#ifndef ZEDO_B200_H
+#define ZEDO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZEDO_B200_ABI_VERSION 1
+
+/* argument errors */
+#define ZEDO_E_INVALID   (-1)  /* NULL pointer / bad enum */
+#define ZEDO_E_SHAPE     (-2)  /* unsupported shape (J, hidden, batch > plan capacity ...) */
+#define ZEDO_E_MISSING   (-3)  /* a state_dict tensor the network needs was not supplied */
+#define ZEDO_E_NOMEM     (-4)  /* host allocation failed */
+#define ZEDO_E_STATE     (-5)  /* call order violated (e.g. step before set_schedule) */
+
+/* GEMM arithmetic of the score network (all accumulate in float32) */
+#define ZEDO_GEMM_SPLIT3 0  /* tcgen05, fp16 hi/lo 3-product split: parity mode (default) */
+#define ZEDO_GEMM_FP16   1  /* tcgen05, single-pass fp16 inputs: fast mode             */
+#define ZEDO_GEMM_FP32   2  /* CUDA-core float32 FFMA: validation kernel                */
+
+/* network kinds */
+#define ZEDO_NET_SCORE_FC_ADV 0  /* ScoreModelFC_Adv          (model.py:97-298)          */
+#define ZEDO_NET_CONTROL      1  /* Control_ScoreModelFC_Adv  (control_model.py:97-382)  */
+
+/* predictors (sampling.py:180-255) and SDEs (sde_lib.py:112-261) for zedo_sde_step */
+#define ZEDO_PRED_EULER_MARUYAMA    0
+#define ZEDO_PRED_REVERSE_DIFFUSION 1
+
+typedef struct zedo_plan zedo_plan;
+
+typedef struct zedo_net_desc {
+  int32_t kind;      /* ZEDO_NET_*                                   */
+  int32_t n_joints;  /* J; 3*J <= 64                                 */
+  int32_t hidden;    /* hidden_dim; must be 1024 (GroupNorm(32, hidden) = groups of 32 channels) */
+  int32_t embed;     /* embed_dim, multiple of 16 (reference: 512)    */
+  int32_t n_blocks;  /* residual blocks (reference: 2)               */
+  float   gn_eps;    /* GroupNorm eps (1e-5)                         */
+} zedo_net_desc;
+
+/* ---- plan: packed weights + workspaces ---------------------------------------------------
+ * Replaces: ScoreModelFC_Adv.__init__/load_state_dict/.to(device) (run/opt_main.py:69-137).
+ * names[i] is a state_dict key ("pre_dense.weight", "b1_gnorm2.bias", ...; a leading
+ * "module." is ignored, run/opt_main.py:130-132) and tensors[i] the float32 data in the
+ * reference layout ([out,in] for Linear weights); host or device pointers are both accepted.
+ * max_batch = largest number of poses a single call will carry.  Synchronises the device. */
+int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tensors,
+                     const char* const* names, const float* const* tensors,
+                     const int64_t* numels, int64_t max_batch, int32_t device);
+int zedo_plan_destroy(zedo_plan* plan);
+int64_t zedo_plan_capacity(const zedo_plan* plan);
+
+/* ---- score network forward -----------------------------------------------------------------
+ * Replaces: ScoreModelFC_Adv.forward(batch, t, condition, mask) (model.py:215-298) in eval
+ * mode for a batch-uniform time label t999 (= 999*t, utils.py:762); condition/mask are never
+ * read by the reference forward.  x, out: [B, J, 3]. */
+int zedo_score_forward(zedo_plan* plan, const float* x, float t999, float* out, int64_t B,
+                       int32_t gemm_mode, void* stream);
+
+/* ---- per-step geometry -----------------------------------------------------------------------
+ * Replaces: gradient_field_gen(key2d, key3d, K, t=T|None, conf=conf|None, returnT=True)
+ * (simple_zeroshot_opt.py:46-125), noise_type=None.
+ * uv [B,J,2], x [B,J,3], K [B,3,3], conf [B,J] or NULL (clamped IN PLACE to [1e-4,1] like
+ * the reference :64-66 when clamp_conf_inplace != 0), T [B,3] in/out: read when solve_T == 0,
+ * written (least-squares solve, sign flip) when solve_T != 0.  g [B,J,3] out (may be NULL);
+ * when x_out != NULL it receives x + g (may alias x). */
+int zedo_grad_field(const float* uv, const float* x, const float* K, float* conf, float* T,
+                    int32_t solve_T, int32_t clamp_conf_inplace, float* g, float* x_out,
+                    int64_t B, int32_t J, void* stream);
+
+/* ---- one predictor update with the network in the loop -------------------------------------
+ * Replaces: pc_sampler(...) (sampling.py:450-527) = NoneCorrector + Predictor.update_fn
+ * (sampling.py:180-205) over RSDE.sde / RSDE.discretize (sde_lib.py:93-107) and get_score_fn
+ * (utils.py:751-777) for the sub-VP SDE.  x [B,J,3] in; x_next, x_mean [B,J,3] out (either
+ * may be NULL or alias x).  z: injected randn_like(x) or NULL (= zeros); ignored when
+ * probability_flow != 0.  t is the continuous time (0.01 .. 0.1 in the shipped configs). */
+int zedo_sde_step(zedo_plan* plan, const float* x, float t, const float* z, int32_t predictor,
+                  int32_t probability_flow, float beta_min, float beta_max, int32_t n_scales,
+                  float* x_next, float* x_mean, int64_t B, int32_t gemm_mode, void* stream);
+
+/* ---- the whole OIL loop ---------------------------------------------------------------------
+ * Replaces: the `for i in range(sample_num)` body of run/opt_main.py:202-220 (and
+ * run/inference.py:211-229): steps x {gradient_field_gen -> x += g -> pc_sampler}, state
+ * resident on the device for all steps.  x [B,J,3] in/out (rotated hypothesis R x0),
+ * T [B,3] in/out, t_sched host float[steps] (= torch.linspace(sde.T, eps, steps)).
+ * Steps i < phase_switch keep T; later steps re-solve it (phase_switch = steps/5 in
+ * opt_main.py:203, 950 in opt_main_infant.py:310).  dump (nullable) [n_dump,B,J,3] receives
+ * the pose after step dump_steps[k] (host int array, ascending). */
+int zedo_oil_loop(zedo_plan* plan, float* x, float* T, const float* uv, const float* K,
+                  float* conf, const float* t_sched, int32_t steps, int32_t phase_switch,
+                  float beta_min, float beta_max, int32_t n_scales, float* dump,
+                  const int32_t* dump_steps, int32_t n_dump, int64_t B, int32_t gemm_mode,
+                  void* stream);
+
+/* ---- IPO: rotation / scale fit ---------------------------------------------------------------
+ * Replaces: T0 (run/opt_main.py:177-179) + RotOpt (simple_zeroshot_opt.py:8-31) +
+ * quaternion_to_matrix (utils.py:59-88) + the 500-iteration Adam loop (run/opt_main.py:180-195)
+ * with the analytic gradient of the mean L1 reprojection loss.
+ * x0 [B,J,3] hypothesis, uv [B,J,2], K [B,3,3], keylist host int[nkey]; axes_mask bit0 = x,
+ * bit1 = y, bit2 = z trainable (config.ZeDO.RotAxes); B_global = batch size of the loss mean
+ * (global batch when poses are sharded).  Outputs R [B,9], T [B,3] = T0*clamp(scale) and
+ * x_rot [B,J,3] = R x0 (may be NULL).  qs (nullable) [B,5] receives (w,x,y,z,scale). */
+int zedo_ipo_fit(const float* x0, const float* uv, const float* K, const int32_t* keylist,
+                 int32_t nkey, int32_t axes_mask, float ipo_T, float minT, float maxT,
+                 int32_t iters, int64_t B_global, float lr, float* R, float* T, float* x_rot,
+                 float* qs, int64_t B, int32_t J, void* stream);
+
+/* RotOpt.forward / its backward for drivers that keep autograd + torch.optim.Adam
+ * (simple_zeroshot_opt.py:20-31).  q [B,4], scale [B], xk [B,nk,3], T0 [B,3], K [B,9];
+ * uv_out [B,nk,2].  Backward: d_uv [B,nk,2] -> d_q [B,4], d_scale [B]. */
+int zedo_rotopt_forward(const float* q, const float* scale, const float* xk, const float* T0,
+                        const float* K, float minT, float maxT, float* uv_out, int64_t B,
+                        int32_t nk, void* stream);
+int zedo_rotopt_backward(const float* q, const float* scale, const float* xk, const float* T0,
+                         const float* K, float minT, float maxT, const float* d_uv, float* d_q,
+                         float* d_scale, int64_t B, int32_t nk, void* stream);
+
+/* ---- evaluation --------------------------------------------------------------------------------
+ * Replaces: eval_multi (lib/dataset/h36m.py:365-442, pw3d.py:286-345) + align_to_gt /
+ * procrustes (lib/utils/transforms.py:42-148).  pred [N,S,J,3] float32, gt [N,J,3] float64
+ * root-relative metres; joint_subset host int[n_sub] or NULL (all J).  Outputs per pose:
+ * err_min [N] float64 = amin over hypotheses of the mean per-joint error (after Procrustes
+ * when protocol2 != 0), argmin [N] int32 (first minimum wins, numpy semantics), and
+ * err_all [N,S] float64 (nullable).  Computed in float64 like the reference's numpy path. */
+int zedo_eval_multi(const float* pred, const double* gt, int32_t protocol2, int64_t N, int32_t S,
+                    int32_t J, const int32_t* joint_subset, int32_t n_sub, double* err_min,
+                    int32_t* argmin, double* err_all, void* stream);
+
+/* ---- misc ---------------------------------------------------------------------------------------- */
+const char* zedo_strerror(int code);
+int zedo_abi_version(void);
+/* number of kernels this library has launched in the calling process (bench.py gpu_launches) */
+int64_t zedo_launch_count(void);
+/* host-side helpers exposed for the CPU test-suite (no GPU needed):
+ * sub-VP scalars in the reference's float32 op order (sde_lib.py:187-198). */
+int zedo_subvp_scalars(float t, float beta_min, float beta_max, float* beta_t, float* diffusion,
+                       float* std);
+/* byte offset of element (row, col) of a [rows, cols] fp16 operand inside the blocked,
+ * 128B-swizzled layout the tcgen05 kernels read (DESIGN.md "data layout"); tile_rows = 128
+ * for activations, 256/64 for weights; hl = 0 (hi) / 1 (lo). */
+int64_t zedo_blocked_offset(int64_t row, int64_t col, int64_t cols, int32_t tile_rows, int32_t hl);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZEDO_B200_H */

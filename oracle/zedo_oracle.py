@@ -38,6 +38,13 @@ T_START = 0.1       # config.model.t  (configs/optim/concat_pose_optimization_h3
 SAMPLING_EPS = 0.01  # config.ZeDO.sampling_eps
 
 
+def _exp32(a):
+    """Correctly rounded float32 exp of a float32 argument.  1 - exp(.) cancels heavily at small t
+    (std ~ 2e-3 at t = 0.01), so a 1-ulp difference between exp implementations (torch/SLEEF,
+    numpy SIMD, glibc, CUDA) shows up as ~3e-5 relative in std: float32 noise of the reference."""
+    return np.exp(np.asarray(a, dtype=np.float64)).astype(f32)
+
+
 def subvp_sde_scalars(t, beta_min=BETA_MIN, beta_max=BETA_MAX):
     """beta(t), diffusion g(t) of ``subVPSDE.sde`` (sde_lib.py:187-192), float32 op order.
 
@@ -46,7 +53,7 @@ def subvp_sde_scalars(t, beta_min=BETA_MIN, beta_max=BETA_MAX):
     t = np.asarray(t, dtype=f32)
     b0, db = f32(beta_min), f32(beta_max - beta_min)
     beta_t = b0 + t * db
-    discount = f32(1.0) - np.exp(f32(-2 * beta_min) * t - db * t ** 2, dtype=f32)
+    discount = f32(1.0) - _exp32(f32(-2 * beta_min) * t - db * t ** 2)
     diffusion = np.sqrt(beta_t * discount, dtype=f32)
     return beta_t.astype(f32), diffusion.astype(f32)
 
@@ -56,7 +63,7 @@ def subvp_marginal_std(t, beta_min=BETA_MIN, beta_max=BETA_MAX):
     t = np.asarray(t, dtype=f32)
     db = f32(beta_max - beta_min)
     lmc = f32(-0.25) * t ** 2 * db - f32(0.5) * t * f32(beta_min)
-    return (f32(1.0) - np.exp(f32(2.0) * lmc, dtype=f32)).astype(f32)
+    return (f32(1.0) - _exp32(f32(2.0) * lmc)).astype(f32)
 
 
 def vp_sde_scalars(t, beta_min=BETA_MIN, beta_max=BETA_MAX):
@@ -496,28 +503,34 @@ def ipo_fit(x0, key2d, K, keylist, rot_axes, ipo_T, minT, maxT, iters=500, b_glo
 # OIL loop                                                      run/opt_main.py:197-222
 # --------------------------------------------------------------------------------------
 
-def oil_loop(W: Weights, x, T, key2d, K, conf, steps=NUM_SCALES, t_start=T_START, eps=SAMPLING_EPS,
-             phase_div=5, dump_every=0, forward=score_forward):
-    """1000 x {gradient_field_gen -> x += g -> pc_sampler} (run/opt_main.py:202-220).
-
-    Phase 1 (i < steps // phase_div) keeps the IPO translation; afterwards T is re-solved
-    each step and carried.  x [B,J,3] is the rotated hypothesis (R x0).  Returns
-    (x_final, T_final, dumps) with dumps = list of (i, x after step i) every dump_every.
-    """
+def oil_loop_schedule(W: Weights, x, T, key2d, K, conf, ts, phase_switch, dump_steps=(), forward=score_forward):
+    """steps x {gradient_field_gen -> x += g -> pc_sampler} (run/opt_main.py:202-220) over an explicit
+    time schedule ``ts``.  Steps i < phase_switch keep the IPO translation; afterwards T is re-solved
+    each step and carried.  Returns (x_final, T_final, {step: pose after that step})."""
     x = x.astype(f32).copy()
     T = T.astype(f32).copy()
-    ts = oil_time_grid(steps, t_start, eps)
-    dumps = []
-    for i in range(steps):
-        if i < steps // phase_div:
+    dumps = {}
+    want = set(int(d) for d in dump_steps)
+    for i in range(len(ts)):
+        if i < phase_switch:
             g, _ = gradient_field(key2d, x, K, t=T, conf=conf)
         else:
             g, T = gradient_field(key2d, x, K, t=None, conf=conf)
         x = (x + g).astype(f32)
         _, x = pc_sampler_step(W, x, ts[i], forward=forward)
-        if dump_every and (i % dump_every == dump_every - 1 or i == 0):
-            dumps.append((i, x.copy()))
+        if i in want:
+            dumps[i] = x.copy()
     return x, T, dumps
+
+
+def oil_loop(W: Weights, x, T, key2d, K, conf, steps=NUM_SCALES, t_start=T_START, eps=SAMPLING_EPS,
+             phase_div=5, dump_every=0, forward=score_forward):
+    """The shipped configuration of the loop: ts = linspace(T, eps, steps), phase switch at steps // 5
+    (run/opt_main.py:197-206).  Returns (x_final, T_final, [(i, pose)] every dump_every steps)."""
+    ts = oil_time_grid(steps, t_start, eps)
+    want = [i for i in range(steps) if dump_every and (i % dump_every == dump_every - 1 or i == 0)]
+    x, T, d = oil_loop_schedule(W, x, T, key2d, K, conf, ts, steps // phase_div, want, forward)
+    return x, T, sorted(d.items())
 
 
 def run_hypothesis(W: Weights, cluster_poses, sid, key2d_conf, K, cfg, fixed_RT=None,

@@ -1,0 +1,65 @@
+"""The C-ABI library loads and exports every symbol include/zedo_b200.h declares; host-side
+helpers agree with the oracle.  No compute call is made (no GPU needed)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+
+import zedo_oracle as zo
+from conftest import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "zedo_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(zedo_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(built_lib):
+    syms = _declared_symbols()
+    assert len(syms) >= 16
+    lib = ctypes.CDLL(built_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/zedo_b200.h but not exported"
+    assert set(syms) == set(built_lib.EXPORTS)
+    assert built_lib.lib.zedo_abi_version() == 1
+
+
+def test_strerror_and_argument_errors(built_lib):
+    assert built_lib.strerror(0) == "ok"
+    assert "invalid" in built_lib.strerror(-1)
+    assert "shape" in built_lib.strerror(-2)
+    # NULL arguments are rejected before any CUDA call
+    assert built_lib.lib.zedo_grad_field(None, None, None, None, None, 0, 0, None, None, 1, 17, None) == -1
+    assert built_lib.lib.zedo_eval_multi(None, None, 0, 1, 1, 17, None, 0, None, None, None, None) == -1
+    assert built_lib.lib.zedo_score_forward(None, None, 0.0, None, 1, 0, None) == -1
+
+
+def test_subvp_scalars_match_oracle(built_lib):
+    for t in zo.oil_time_grid():
+        b, g, s = built_lib.subvp_scalars(float(t))
+        bo, go = zo.subvp_sde_scalars(t)
+        so = zo.subvp_marginal_std(t)
+        assert b == float(bo) and g == float(go) and s == float(so)  # same float32 op order, bit-exact
+
+
+def test_blocked_layout_is_a_swizzled_bijection(built_lib):
+    """Every (row, col, hl) of a [256, 128] operand maps to a distinct 2-byte slot; a row's eight
+    16-byte chunks are permuted by c ^ (row & 7) inside its 128-byte line (TMA SWIZZLE_128B)."""
+    rows, cols, tile = 256, 128, 128
+    seen = set()
+    for r in range(rows):
+        for c in range(cols):
+            for hl in (0, 1):
+                seen.add(built_lib.blocked_offset(r, c, cols, tile, hl))
+    assert len(seen) == rows * cols * 2 and min(seen) == 0 and max(seen) == rows * cols * 2 * 2 - 2
+    for r in (0, 1, 5, 7, 8, 13, 127, 128, 200):
+        base = built_lib.blocked_offset(r, 0, cols, tile, 0) & ~127
+        for chunk in range(8):
+            off = built_lib.blocked_offset(r, chunk * 8, cols, tile, 0)
+            assert off - base == ((chunk ^ (r & 7)) * 16)
+    # tile (rt, kb) images are contiguous: hi image then lo image, 16 KiB each
+    assert built_lib.blocked_offset(0, 0, cols, tile, 1) - built_lib.blocked_offset(0, 0, cols, tile, 0) == 16384
+    assert built_lib.blocked_offset(0, 64, cols, tile, 0) == 32768
+    assert built_lib.blocked_offset(128, 0, cols, tile, 0) == 65536

@@ -1,0 +1,341 @@
+"""Parity of the CUDA kernels (through the C ABI) against the oracle and the golden vectors.
+
+All tests need a B200 (-m gpu).  Tolerances: float32 paths 1e-4 relative to the tensor maximum
+(north_star: "per-step poses within 1e-4 relative in fp32"), evaluation 1e-9 absolute, selection
+indices bit-exact.
+"""
+import numpy as np
+import pytest
+
+import zedo_oracle as zo
+from conftest import rel_err
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def zr():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device: there is no CPU fallback")
+    import __graft_entry__ as g
+    g.build()
+    import zedo_release_b200 as zr
+    torch.cuda.set_device(0)
+    return zr
+
+
+def dev(a, dtype=torch.float32):
+    return torch.tensor(np.ascontiguousarray(a), dtype=dtype, device="cuda")
+
+
+@pytest.fixture(scope="module")
+def plan17(zr):
+    p = zr.ScorePlan(zo.make_weights(seed=0), n_joints=17, max_batch=4096, device=0)
+    yield p
+    p.close()
+
+
+# ---- geometry (K3) ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,use_t,use_conf", [("fixedT_conf", True, True), ("solveT_conf", False, True),
+                                               ("solveT_noconf", False, False), ("fixedT_noconf", True, False)])
+def test_grad_field_golden(zr, golden, tag, use_t, use_conf):
+    g = golden("geom")
+    conf = dev(g["db_2d"][:, :, 2]) if use_conf else None
+    grad, T = zr.grad_field(dev(g["db_2d"][:, :, :2]), dev(g["x"]), dev(g["K"]), conf=conf,
+                            T=dev(g["T_in"]) if use_t else None)
+    assert rel_err(grad.cpu().numpy(), g[f"{tag}_g"]) < 1e-4
+    assert rel_err(T.cpu().numpy(), g[f"{tag}_T"]) < 1e-4
+    if use_conf:  # clamped in place like the reference (simple_zeroshot_opt.py:64-66)
+        c = conf.cpu().numpy()
+        assert c.max() <= 1.0 and c.min() >= np.float32(1e-4)
+        assert c[0, 3] == 1.0 and c[1, 5] == np.float32(1e-4)
+
+
+def test_grad_field_sign_flip_and_demo(zr, golden):
+    g = golden("geom")
+    grad, T = zr.grad_field(dev(g["db_2d"][:, :, :2]), dev(g["x_neg"]), dev(g["K"]))
+    assert rel_err(grad.cpu().numpy(), g["flip_g"]) < 2e-4 and rel_err(T.cpu().numpy(), g["flip_T"]) < 1e-4
+    assert (T.cpu().numpy()[:, :, 2] >= 0).all()
+    d = golden("demo")  # the reference's only known answer: 53.63671875 (simple_zeroshot_opt.py:127-147)
+    k3 = dev(d["key3d"])
+    first = None
+    for i in range(10):
+        gr, _ = zr.grad_field(dev(d["key2d"]), k3, dev(d["K"]))
+        if i == 0:
+            first = float(torch.mean(torch.norm(gr, dim=-1)))
+        k3 = k3 + gr
+    assert abs(first - 53.63671875) / 53.63671875 < 1e-5
+    assert rel_err(k3.cpu().numpy(), d["final_key3d"]) < 1e-5
+
+
+@pytest.mark.parametrize("J,B", [(17, 1000), (12, 333), (1, 5), (32, 64)])
+def test_grad_field_vs_oracle_random(zr, J, B):
+    ds = zo.make_synthetic_dataset(B, n_joints=J, seed=J * 7 + 1)
+    x = (ds["db_3d"] + np.random.default_rng(J).normal(0, 0.05, ds["db_3d"].shape)).astype(np.float32)
+    uv, K, conf = ds["db_2d"][:, :, :2], ds["camera_param"], ds["db_2d"][:, :, 2]
+    if J >= 4:
+        g_o, T_o = zo.gradient_field(uv, x, K, conf=conf.copy())
+        g_g, T_g = zr.grad_field(dev(uv), dev(x), dev(K), conf=dev(conf))
+        assert rel_err(g_g.cpu().numpy(), g_o) < 1e-4 and rel_err(T_g.cpu().numpy(), T_o) < 1e-4
+    T_in = zo.init_translation(uv, K, 3.0)
+    g_o, _ = zo.gradient_field(uv, x, K, t=T_in, conf=None)
+    g_g, T_back = zr.grad_field(dev(uv), dev(x), dev(K), T=dev(T_in))
+    assert rel_err(g_g.cpu().numpy(), g_o) < 1e-4
+    assert np.array_equal(T_back.cpu().numpy(), T_in)
+
+
+def test_grad_field_empty_batch(zr):
+    e = torch.empty((0, 17, 3), device="cuda")
+    g, T = zr.grad_field(torch.empty((0, 17, 2), device="cuda"), e, torch.empty((0, 3, 3), device="cuda"))
+    assert g.shape == (0, 17, 3) and T.shape == (0, 1, 3)
+
+
+# ---- score network (K1) -------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("split3", 2e-5), ("fp16", 3e-3)])
+def test_score_forward_golden(zr, golden, plan17, mode, tol):
+    g = golden("net")
+    for t in (0.1, 0.05, 0.01):
+        out = plan17.forward(dev(g["x"]), float(np.float32(t) * np.float32(999)), mode=mode)
+        assert rel_err(out.cpu().numpy(), g[f"out_{t}"]) < tol, (mode, t)
+
+
+@pytest.mark.parametrize("B", [1, 127, 128, 129, 300, 4096])
+def test_score_forward_vs_oracle_ragged_batches(zr, plan17, B):
+    W = zo.make_weights(seed=0)
+    x = np.random.default_rng(B).normal(0, 0.4, (B, 17, 3)).astype(np.float32)
+    ref = zo.score_forward(W, x, np.float32(33.3))
+    fp32 = plan17.forward(dev(x), 33.3, mode="fp32").cpu().numpy()
+    tc = plan17.forward(dev(x), 33.3, mode="split3").cpu().numpy()
+    assert rel_err(fp32, ref) < 2e-5
+    assert rel_err(tc, ref) < 2e-5
+    assert rel_err(tc, fp32) < 2e-5  # tcgen05 path against the CUDA-core validation kernel, on device
+
+
+def test_score_forward_j12_and_block_count(zr, golden):
+    g = golden("net12")
+    W = zo.make_weights(seed=int(g["weights_seed"]), n_joints=12)
+    p = zr.ScorePlan(W, n_joints=12, max_batch=64, device=0)
+    out = p.forward(dev(g["x"]), float(g["t999"]), mode="split3")
+    assert rel_err(out.cpu().numpy(), g["out"]) < 2e-5
+    p.close()
+    W2 = zo.make_weights(seed=5, embed=64, n_blocks=1)
+    p2 = zr.ScorePlan(W2, n_joints=17, embed=64, n_blocks=1, max_batch=200, device=0)
+    x = np.random.default_rng(1).normal(0, 0.4, (200, 17, 3)).astype(np.float32)
+    ref = zo.score_forward(W2, x, np.float32(12.0), n_blocks=1)
+    assert rel_err(p2.forward(dev(x), 12.0, mode="split3").cpu().numpy(), ref) < 2e-5
+    p2.close()
+    from zedo_release_b200._native import ZedoError
+    with pytest.raises(ZedoError) as e:  # hidden != 1024 is rejected, not silently mis-normalised
+        zr.ScorePlan(zo.make_weights(seed=5, hidden=256), n_joints=17, hidden=256, max_batch=8, device=0)
+    assert e.value.code == -2
+
+
+def test_plan_errors(zr, plan17):
+    from zedo_release_b200._native import ZedoError
+    W = zo.make_weights(seed=0)
+    bad = dict(W)
+    del bad["b1_dense2_t.weight"]
+    with pytest.raises(ZedoError) as e:
+        zr.ScorePlan(bad, n_joints=17, max_batch=8, device=0)
+    assert e.value.code == -3
+    with pytest.raises(ZedoError) as e:
+        plan17.forward(torch.zeros((plan17.capacity + 1, 17, 3), device="cuda"), 1.0)
+    assert e.value.code == -2
+    with pytest.raises(ValueError):
+        plan17.forward(torch.zeros((4, 17, 3)), 1.0)  # CPU tensor: no CPU path
+
+
+# ---- sampler step (K2) ----------------------------------------------------------------------------------
+def test_sde_step_golden(zr, golden, plan17):
+    g, n = golden("sampler"), golden("noise")
+    x = dev(g["x"])
+    xn, xm = plan17.sde_step(x, float(g["t"]), mode="split3")
+    assert rel_err(xm.cpu().numpy(), g["results"]) < 1e-5 and rel_err(xn.cpu().numpy(), g["results"]) < 1e-5
+    xn, xm = plan17.sde_step(x, float(g["t"]), z=dev(n["z"]), probability_flow=False, mode="split3")
+    assert rel_err(xn.cpu().numpy(), n["em_x"]) < 1e-5 and rel_err(xm.cpu().numpy(), n["em_mean"]) < 1e-5
+    xn, xm = plan17.sde_step(x, float(g["t"]), z=dev(n["z"]), predictor="reverse_diffusion", probability_flow=False,
+                             mode="split3")
+    assert rel_err(xn.cpu().numpy(), n["rd_x"]) < 1e-5 and rel_err(xm.cpu().numpy(), n["rd_mean"]) < 1e-5
+
+
+# ---- OIL loop ---------------------------------------------------------------------------------------------
+def _oil_inputs(golden):
+    g, geo = golden("oil"), golden("geom")
+    x_rot = np.einsum("bij,bnj->bni", g["R"], g["x0"]).astype(np.float32)
+    return g, geo, x_rot
+
+
+def test_oil_teacher_forced_golden(zr, golden, plan17):
+    """One loop step restarted from the reference's own state after step 499 (phase 2: T re-solved)."""
+    g, geo = golden("tf500"), golden("geom")
+    x, T = dev(g["x_in"]), torch.zeros((16, 3), device="cuda")
+    plan17.oil_loop(x, T, dev(geo["db_2d"][:, :, :2]), dev(geo["K"]), dev(geo["db_2d"][:, :, 2]), [float(g["t"])],
+                    phase_switch=0, mode="split3")
+    assert rel_err(x.cpu().numpy(), g["x_out"]) < 1e-5
+    assert rel_err(T.cpu().numpy(), g["T_out"].reshape(16, 3)) < 1e-5
+
+
+@pytest.mark.parametrize("mode", ["split3", "fp32"])
+def test_oil_teacher_forced_every_step(zr, golden, plan17, mode):
+    """Per-step parity (north_star: 1e-4 relative): every one of 60 consecutive steps across the phase
+    switch, each restarted from the GPU's own previous state, against the oracle."""
+    g, geo, x_rot = _oil_inputs(golden)
+    W = zo.make_weights(seed=0)
+    steps, switch = 60, 30
+    ts = zo.oil_time_grid()[170:170 + steps]
+    uv, K, conf = geo["db_2d"][:, :, :2], geo["K"], geo["db_2d"][:, :, 2]
+    x, T = dev(x_rot), dev(g["T"].reshape(16, 3))
+    dump = plan17.oil_loop(x, T, dev(uv), dev(K), dev(conf), ts, phase_switch=switch, dump_steps=range(steps),
+                           mode=mode).cpu().numpy()
+    prev, T_o = x_rot, g["T"]
+    worst = 0.0
+    conf_c = conf.copy()
+    for i in range(steps):
+        if i < switch:
+            gr, _ = zo.gradient_field(uv, prev, K, t=T_o, conf=conf_c)
+        else:
+            gr, T_o = zo.gradient_field(uv, prev, K, conf=conf_c)
+        _, nxt = zo.pc_sampler_step(W, (prev + gr).astype(np.float32), ts[i])
+        worst = max(worst, rel_err(dump[i], nxt))
+        prev = dump[i]
+    assert worst < 1e-5, worst
+    assert rel_err(T.cpu().numpy(), T_o.reshape(16, 3)) < 1e-4
+
+
+def test_oil_full_loop_golden(zr, golden, plan17):
+    """The complete 1000-step loop against the reference's trajectory.  Two float32 implementations
+    that agree to 1e-6 per step drift apart cumulatively (tests/golden/PINNING.txt records 7e-4
+    between numpy and torch); the bound that matters downstream is the final MPJPE: 0.1 mm."""
+    g, geo, x_rot = _oil_inputs(golden)
+    uv, K, conf = geo["db_2d"][:, :, :2], geo["K"], geo["db_2d"][:, :, 2]
+    x, T = dev(x_rot), dev(g["T"].reshape(16, 3))
+    steps = [int(s) for s in g["steps"]]
+    dump = plan17.oil_loop(x, T, dev(uv), dev(K), dev(conf), zo.oil_time_grid(), dump_steps=steps,
+                           mode="split3").cpu().numpy()
+    for k, s in enumerate(steps):
+        assert rel_err(dump[k], g["poses"][k]) < 3e-3, s
+    assert rel_err(dump[0], g["poses"][0]) < 1e-5
+    assert rel_err(T.cpu().numpy(), g["T_final"].reshape(16, 3)) < 3e-3
+    gt = zo.make_synthetic_dataset(16, seed=7, n_clusters=3)["db_3d"].astype(np.float64)
+    m_gpu = np.mean([zo.mpjpe(dump[-1][n], gt[n]) for n in range(16)])
+    m_ref = np.mean([zo.mpjpe(g["poses"][-1][n], gt[n]) for n in range(16)])
+    assert abs(m_gpu - m_ref) < 1e-4  # metres: 0.1 mm
+
+
+def test_oil_rows_are_independent(zr, plan17):
+    """Sharding property: running two halves separately is bit-identical to the full batch."""
+    B = 1000
+    ds = zo.make_synthetic_dataset(B, seed=3)
+    uv, K, conf = dev(ds["db_2d"][:, :, :2]), dev(ds["camera_param"]), dev(ds["db_2d"][:, :, 2])
+    x0 = dev(ds["db_3d"] + 0.1)
+    T0 = dev(zo.init_translation(ds["db_2d"][:, :, :2], ds["camera_param"], 3.0).reshape(B, 3))
+    ts = zo.oil_time_grid()[195:205]
+    xa, Ta = x0.clone(), T0.clone()
+    plan17.oil_loop(xa, Ta, uv, K, conf.clone(), ts, phase_switch=5)
+    parts = []
+    for lo, hi in ((0, 437), (437, B)):
+        xb, Tb = x0[lo:hi].clone(), T0[lo:hi].clone()
+        plan17.oil_loop(xb, Tb, uv[lo:hi].contiguous(), K[lo:hi].contiguous(), conf[lo:hi].clone(), ts, phase_switch=5)
+        parts.append(xb)
+    assert torch.equal(torch.cat(parts), xa)
+
+
+# ---- IPO (K4) ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,cfg", [("h36m", zo.H36M_ZEDO_CFG), ("mini", zo.MINI_ZEDO_CFG)])
+def test_ipo_short_trajectory_golden(zr, golden, tag, cfg):
+    g, geo = golden("ipo"), golden("geom")
+    uv, K = geo["db_2d"][:, :, :2], geo["K"]
+    for iters in (1, 10):
+        R, T, x_rot, qs = zr.ipo_fit(dev(g[f"{tag}_x0"]), dev(uv), dev(K), cfg["IPO_keylist"], cfg["RotAxes"],
+                                     cfg["IPO_T"], cfg["IPO_minScaleT"], cfg["IPO_maxScaleT"], iters=iters)
+        qs = qs.cpu().numpy()
+        assert rel_err(qs[:, :4], g[f"{tag}_q_traj"][iters - 1]) < 1e-4
+        assert rel_err(qs[:, 4], g[f"{tag}_s_traj"][iters - 1]) < 1e-4
+        assert rel_err(R.cpu().numpy(), zo.quaternion_to_matrix(qs[:, :4])) < 1e-6
+        assert rel_err(x_rot.cpu().numpy(), np.einsum("bij,bnj->bni", R.cpu().numpy(), g[f"{tag}_x0"])) < 1e-6
+    # 500 iterations: L1 + Adam(lr 0.1) is chaotic, so compare the loss level, not the trajectory
+    R, T, x_rot, qs = zr.ipo_fit(dev(g[f"{tag}_x0"]), dev(uv), dev(K), cfg["IPO_keylist"], cfg["RotAxes"],
+                                 cfg["IPO_T"], cfg["IPO_minScaleT"], cfg["IPO_maxScaleT"], iters=500)
+    qs = qs.cpu().numpy()
+    kl = cfg["IPO_keylist"]
+    uv_o, _, _ = zo.ipo_project(qs[:, :4], qs[:, 4], g[f"{tag}_x0"][:, kl], g[f"{tag}_T0"], K, cfg["IPO_minScaleT"],
+                                cfg["IPO_maxScaleT"])
+    loss = float(np.abs(uv_o - uv[:, kl]).mean())
+    assert abs(loss - g[f"{tag}_loss"][-1]) / g[f"{tag}_loss"][-1] < 0.05
+    Tc = g[f"{tag}_T0"][:, 0] * np.clip(qs[:, 4], cfg["IPO_minScaleT"], cfg["IPO_maxScaleT"])[:, None]
+    assert rel_err(T.cpu().numpy(), Tc) < 1e-6
+
+
+@pytest.mark.parametrize("axes,nk", [("z", 3), ("xyz", 17), ("y", 12)])
+def test_rotopt_forward_backward_vs_oracle(zr, axes, nk):
+    B = 257
+    rng = np.random.default_rng(nk)
+    ds = zo.make_synthetic_dataset(B, seed=nk)
+    kl = list(range(nk))
+    xk = ds["db_3d"][:, kl].astype(np.float32)
+    K = ds["camera_param"]
+    T0 = zo.init_translation(ds["db_2d"][:, :, :2], K, 3.0)
+    q = rng.normal(0, 0.3, (B, 4)).astype(np.float32)
+    q[:, 0] += 1
+    scale = rng.uniform(0.3, 2.5, B).astype(np.float32)  # some outside the clamp [0.5, 2]
+    uv_o, _, _ = zo.ipo_project(q, scale, xk, T0, K, 0.5, 2.0)
+    uv_g = zr.rotopt_forward(dev(q), dev(scale), dev(xk), dev(T0.reshape(B, 3)), dev(K), 0.5, 2.0)
+    assert rel_err(uv_g.cpu().numpy(), uv_o) < 1e-5
+    # gradient of mean |uv - uv*|: oracle analytic gradient (pinned against autograd by gen_golden.py)
+    uv_t = ds["db_2d"][:, kl, :2]
+    mask = zo.axes_to_mask("xyz")
+    _, dq_o, ds_o = zo.ipo_loss_and_grad(q, scale, xk, uv_t, T0, K, 0.5, 2.0, mask)
+    d_uv = (np.sign(uv_o - uv_t) / (B * nk * 2)).astype(np.float32)
+    dq_g, ds_g = zr.rotopt_backward(dev(q), dev(scale), dev(xk), dev(T0.reshape(B, 3)), dev(K), 0.5, 2.0, dev(d_uv))
+    assert rel_err(dq_g.cpu().numpy(), dq_o) < 1e-4
+    assert rel_err(ds_g.cpu().numpy(), ds_o) < 1e-4
+
+
+# ---- evaluation (K5) -------------------------------------------------------------------------------------------
+def test_eval_multi_golden(zr, golden):
+    g = golden("eval")
+    pred, gt = dev(g["preds"]), dev(g["gts"], torch.float64)
+    for p2 in (0, 1):
+        e, idx, e_all = zr.eval_multi(pred, gt, protocol2=bool(p2), return_all=True)
+        assert np.abs(e.cpu().numpy() - g[f"min_p{p2}"]).max() < 1e-9
+        assert np.array_equal(idx.cpu().numpy(), g[f"idx_p{p2}"])  # bit-exact selection
+        agg = zr.aggregate_errors(e, g["actions"])
+        assert abs(agg - float(g[f"agg_p{p2}"])) < 1e-9
+        assert np.abs(e_all.cpu().numpy().min(axis=1) - g[f"min_p{p2}"]).max() < 1e-9
+    assert abs(zr.aggregate_errors(zr.eval_multi(pred, gt, protocol2=True)[0]) - float(g["agg_pw3d_p1"])) < 1e-9
+
+
+def test_eval_multi_large_random_and_subset(zr):
+    rng = np.random.default_rng(0)
+    N, S, J = 500, 7, 17
+    gts = rng.normal(0, 0.3, (N, J, 3))
+    gts -= gts[:, 0:1]
+    preds = (gts[:, None] + rng.normal(0, 0.08, (N, S, J, 3))).astype(np.float32)
+    preds[::9, 3] = preds[::9, 1]  # ties: first index must win
+    sub = [1, 2, 3, 4, 5, 6, 8, 10, 11, 12, 13, 14]
+    for p2 in (False, True):
+        _, res, idx = zo.eval_multi(preds, gts, protocol2=p2)
+        e, i = zr.eval_multi(dev(preds), dev(gts, torch.float64), protocol2=p2)
+        assert np.abs(e.cpu().numpy() - res).max() < 1e-9
+        assert np.array_equal(i.cpu().numpy(), idx)
+        _, res_s, idx_s = zo.eval_multi(preds, gts, protocol2=p2, joint_subset=sub)
+        e, i = zr.eval_multi(dev(preds), dev(gts, torch.float64), protocol2=p2, joint_subset=sub)
+        assert np.abs(e.cpu().numpy() - res_s).max() < 1e-9
+        assert np.array_equal(i.cpu().numpy(), idx_s)
+
+
+# ---- whole pipeline ----------------------------------------------------------------------------------------------
+def test_pipeline_shapes_and_quality(zr, plan17):
+    """IPO + a shortened OIL loop + eval through the public runner: finite, and the reprojection fit
+    brings every joint onto its camera ray (|gradient| ~ 0 after one projection)."""
+    B, S = 300, 2
+    ds = zo.make_synthetic_dataset(B, seed=21, n_clusters=S)
+    cfg = dict(zo.H36M_ZEDO_CFG)
+    res = zr.run_pose_optimisation(plan17, dev(ds["db_2d"]), dev(ds["camera_param"]), dev(ds["clusters"]), cfg,
+                                   hypo=S, steps=25)
+    assert res.shape == (B, S, 17, 3) and torch.isfinite(res).all()
+    e1, i1 = zr.eval_multi(res, dev(ds["db_3d"], torch.float64), protocol2=False)
+    e2, i2 = zr.eval_multi(res, dev(ds["db_3d"], torch.float64), protocol2=True)
+    assert (e2 <= e1 + 1e-12).all()  # Procrustes alignment never increases the error
+    assert set(i1.cpu().numpy().tolist()) <= {0, 1}

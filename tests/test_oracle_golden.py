@@ -1,0 +1,132 @@
+"""The oracle (oracle/zedo_oracle.py) against the golden vectors that oracle/gen_golden.py wrote
+from the imported reference.  Runs without the reference tree and without a GPU."""
+import numpy as np
+import pytest
+
+import zedo_oracle as zo
+from conftest import rel_err
+
+
+def test_time_grid_and_sde_scalars(golden):
+    g = golden("sde")
+    assert np.array_equal(zo.oil_time_grid(), g["time_grid"])  # bit-exact torch.linspace
+    beta, diff = zo.subvp_sde_scalars(g["t"])
+    assert rel_err(diff, g["diffusion"]) < 2e-5
+    assert rel_err(0.5 * beta, g["half_beta"]) < 2e-7
+    assert rel_err(zo.subvp_marginal_std(g["t"]), g["std"]) < 1e-4  # 1 - exp(.) cancellation, see _exp32
+    # SURVEY 8c probe values
+    for t, g2, sig in ((0.1, 0.411058, 0.103718), (0.05, 0.063510, 0.029433), (0.01, 0.00119064, 0.00199300)):
+        _, d = zo.subvp_sde_scalars(np.float32(t))
+        assert abs(float(d) ** 2 - g2) / g2 < 1e-4
+        assert abs(float(zo.subvp_marginal_std(np.float32(t))) - sig) / sig < 1e-4
+
+
+def test_reference_demo_known_answer(golden):
+    """The only known-answer test the reference ships: simple_zeroshot_opt.py:127-147."""
+    g = golden("demo")
+    k3 = g["key3d"].copy()
+    first = None
+    for i in range(10):
+        grad, _ = zo.gradient_field(g["key2d"], k3, g["K"])
+        if i == 0:
+            first = float(np.mean(np.linalg.norm(grad, axis=-1)))
+        k3 = k3 + grad
+    assert float(g["first_norm"]) == 53.63671875
+    assert abs(first - 53.63671875) / 53.63671875 < 1e-6
+    assert rel_err(k3, g["final_key3d"]) < 1e-6
+
+
+@pytest.mark.parametrize("tag,use_t,use_conf", [("fixedT_conf", True, True), ("solveT_conf", False, True),
+                                               ("solveT_noconf", False, False), ("fixedT_noconf", True, False)])
+def test_gradient_field(golden, tag, use_t, use_conf):
+    g = golden("geom")
+    conf = g["db_2d"][:, :, 2].copy() if use_conf else None
+    grad, T = zo.gradient_field(g["db_2d"][:, :, :2], g["x"], g["K"], t=g["T_in"] if use_t else None, conf=conf)
+    assert rel_err(grad, g[f"{tag}_g"]) < 2e-5
+    assert rel_err(T, g[f"{tag}_T"]) < 2e-5
+    if use_conf:
+        assert conf.max() <= 1.0 and conf.min() >= np.float32(1e-4)  # clamped in place
+
+
+def test_gradient_field_sign_flip(golden):
+    g = golden("geom")
+    grad, T = zo.gradient_field(g["db_2d"][:, :, :2], g["x_neg"], g["K"])
+    assert rel_err(grad, g["flip_g"]) < 1e-4 and rel_err(T, g["flip_T"]) < 2e-5
+    assert (T[:, :, 2] >= 0).all()
+
+
+def test_score_network(golden):
+    g = golden("net")
+    W = zo.make_weights(seed=int(g["weights_seed"]))
+    for t in (0.1, 0.05, 0.01):
+        out = zo.score_forward(W, g["x"], np.float32(t) * np.float32(999))
+        assert rel_err(out, g[f"out_{t}"]) < 2e-5
+    g12 = golden("net12")
+    W12 = zo.make_weights(seed=int(g12["weights_seed"]), n_joints=12)
+    assert rel_err(zo.score_forward(W12, g12["x"], g12["t999"]), g12["out"]) < 2e-5
+
+
+def test_control_network(golden):
+    g = golden("control")
+    W = zo.make_weights(seed=int(g["weights_seed"]), control=True)
+    assert rel_err(zo.control_score_forward(W, g["x"], g["t999"]), g["out"]) < 2e-5
+
+
+def test_sampler_steps(golden):
+    g, n = golden("sampler"), golden("noise")
+    W = zo.make_weights(seed=0)
+    trajs, res = zo.pc_sampler_step(W, g["x"], g["t"])
+    assert rel_err(res, g["results"]) < 2e-6 and rel_err(trajs, g["trajs"]) < 2e-6
+    x, xm = zo.euler_maruyama_update(W, g["x"], g["t"], z=n["z"], probability_flow=False)
+    assert rel_err(x, n["em_x"]) < 2e-6 and rel_err(xm, n["em_mean"]) < 2e-6
+    x, xm = zo.reverse_diffusion_update(W, g["x"], g["t"], z=n["z"], probability_flow=False)
+    assert rel_err(x, n["rd_x"]) < 2e-6 and rel_err(xm, n["rd_mean"]) < 2e-6
+
+
+@pytest.mark.parametrize("tag,cfg", [("h36m", zo.H36M_ZEDO_CFG), ("mini", zo.MINI_ZEDO_CFG)])
+def test_ipo_short_trajectory(golden, tag, cfg):
+    g, geo = golden("ipo"), golden("geom")
+    trace = []
+    zo.ipo_fit(g[f"{tag}_x0"], geo["db_2d"][:, :, :2], geo["K"], cfg["IPO_keylist"], cfg["RotAxes"], cfg["IPO_T"],
+               cfg["IPO_minScaleT"], cfg["IPO_maxScaleT"], iters=10, trace=trace)
+    assert rel_err(trace[9][0], g[f"{tag}_q_traj"][9]) < 2e-5
+    assert rel_err(trace[9][1], g[f"{tag}_s_traj"][9]) < 2e-5
+    assert rel_err(zo.quaternion_to_matrix(g[f"{tag}_q_final"]), g[f"{tag}_R_final"]) < 1e-6
+
+
+def test_oil_teacher_forced_step(golden):
+    g, geo = golden("tf500"), golden("geom")
+    W = zo.make_weights(seed=0)
+    grad, T = zo.gradient_field(geo["db_2d"][:, :, :2], g["x_in"], geo["K"], conf=geo["db_2d"][:, :, 2].copy())
+    _, out = zo.pc_sampler_step(W, (g["x_in"] + grad).astype(np.float32), g["t"])
+    assert rel_err(out, g["x_out"]) < 1e-5 and rel_err(T, g["T_out"]) < 1e-5
+
+
+def test_oil_loop_first_steps(golden):
+    """Cumulative parity over the first 100 steps (the full 1000-step loop is pinned by
+    oracle/gen_golden.py; here the run is kept short for the CPU suite)."""
+    g, geo = golden("oil"), golden("geom")
+    W = zo.make_weights(seed=0)
+    x_rot = np.einsum("bij,bnj->bni", g["R"], g["x0"]).astype(np.float32)
+    ts = zo.oil_time_grid()[:100]
+    _, _, d = zo.oil_loop_schedule(W, x_rot, g["T"], geo["db_2d"][:, :, :2], geo["K"], geo["db_2d"][:, :, 2].copy(),
+                                   ts, 200, dump_steps=(0, 9, 99))
+    steps = list(g["steps"])
+    for s, tol in ((0, 5e-6), (9, 5e-5), (99, 5e-4)):
+        assert rel_err(d[s], g["poses"][steps.index(s)]) < tol
+
+
+def test_procrustes_and_eval_multi(golden):
+    g = golden("eval")
+    preds, gts = g["preds"], g["gts"]
+    N, S = preds.shape[:2]
+    al = np.stack([zo.procrustes_align(preds[n, s], gts[n]) for n in range(N) for s in range(S)])
+    assert rel_err(al, g["aligned"]) < 1e-9
+    for p2 in (0, 1):
+        agg, res, idx = zo.eval_multi(preds, gts, protocol2=bool(p2), actions=g["actions"])
+        assert abs(agg - float(g[f"agg_p{p2}"])) < 1e-12
+        assert np.abs(res - g[f"min_p{p2}"]).max() < 1e-12
+        assert np.array_equal(idx, g[f"idx_p{p2}"])  # selection indices bit-exact
+    assert g["idx_p0"][5] == 0  # exact tie -> first index wins
+    agg, _, _ = zo.eval_multi(preds, gts, protocol2=True)
+    assert abs(agg - float(g["agg_pw3d_p1"])) < 1e-12

@@ -1,0 +1,553 @@
+// C ABI of the library (include/zedo_b200.h): plan construction (weight packing, workspaces,
+// per-step bias tables) and the orchestration of the kernels.  Host code only; every kernel
+// lives in its own translation unit.
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace zedo {
+
+static std::atomic<int64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// sub-VP scalars, float32 op order of the reference (sde_lib.py:187-198)
+SdeCoef subvp_coef(float t, float beta_min, float beta_max, int n_scales) {
+  SdeCoef c;
+  const float db = (float)((double)beta_max - (double)beta_min);
+  c.beta_t = beta_min + t * db;
+  const float m2b0 = (float)(-2.0 * (double)beta_min);
+  const float discount = 1.0f - expf(m2b0 * t - db * (t * t));
+  c.diffusion = sqrtf(c.beta_t * discount);
+  const float lmc = -0.25f * (t * t) * db - 0.5f * t * beta_min;
+  c.std = 1.0f - expf(2.0f * lmc);
+  c.dt = (float)(-1.0 / (double)n_scales);
+  return c;
+}
+
+// ---- host-side weight packing ------------------------------------------------------------------------
+struct PackedWeight {
+  __half* dev = nullptr;  // blocked hi/lo [N_pad, K_pad]
+  float descale = 1.f;
+  int n_pad = 0, k_pad = 0, bn = 0;
+};
+
+static float pow2_scale_for(const float* w, int64_t n) {
+  float mx = 0.f;
+  for (int64_t i = 0; i < n; ++i) mx = std::fmax(mx, std::fabs(w[i]));
+  if (!(mx > 0.f) || !std::isfinite(mx)) return 1.f;
+  int e;
+  std::frexp(mx, &e);  // mx = f * 2^e, f in [0.5, 1)  ->  mx * 2^(9-e) in [256, 512)
+  return std::ldexp(1.f, 9 - e);
+}
+
+static int pack_weight(const float* w, int N, int K, int bn, PackedWeight* out) {
+  const int n_pad = (int)round_up(N, bn), k_pad = (int)round_up(K, kBlockK);
+  const float s = pow2_scale_for(w, (int64_t)N * K);
+  std::vector<__half> buf((size_t)n_pad * k_pad * 2, __float2half_rn(0.f));
+  for (int n = 0; n < N; ++n) {
+    for (int k = 0; k < K; ++k) {
+      const float v = w[(int64_t)n * K + k] * s;
+      const __half hi = __float2half_rn(v);
+      const __half lo = __float2half_rn(v - __half2float(hi));
+      buf[(size_t)blocked_half_offset(n, k, k_pad, bn, 0)] = hi;
+      buf[(size_t)blocked_half_offset(n, k, k_pad, bn, 1)] = lo;
+    }
+  }
+  ZEDO_CUDA_TRY(cudaMalloc(&out->dev, buf.size() * sizeof(__half)));
+  ZEDO_CUDA_TRY(cudaMemcpy(out->dev, buf.data(), buf.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  out->descale = 1.f / s;
+  out->n_pad = n_pad;
+  out->k_pad = k_pad;
+  out->bn = bn;
+  return 0;
+}
+
+struct GemmOp {
+  int weight;      // index into plan->packed / plan->w32
+  int in_buf;      // -1 = xa (first operand), else activation buffer index
+  int out_buf;     // activation buffer index, -1 = eps (float32)
+  int table_row;   // row of the per-step bias table, -1 = static bias (post_dense)
+  int gn;          // GroupNorm index, -1 = none
+  int resid_buf;   // -1 = none
+  int addend_buf;  // -1 = none
+  int epi;
+};
+
+}  // namespace zedo
+
+using namespace zedo;
+
+struct zedo_plan {
+  zedo_net_desc desc{};
+  int device = 0, num_sms = 148;
+  int D = 0, H = 0, E = 0, L = 0;  // L = rows of the bias table (layers with a time projection)
+  int64_t cap = 0, m_pad = 0;
+
+  // float32 device copies
+  std::vector<float*> w32;  // per GEMM weight, reference layout [N, K] (validation mode + sizes)
+  std::vector<int> w_n, w_k;
+  float* Ws = nullptr;      // shared_time_embed.0.weight [E,E]
+  float* bs = nullptr;      // [E]
+  float* Wt_cat = nullptr;  // [L*H, E]: the `*_t` projections, concatenated
+  float* bt_cat = nullptr;  // [L*H]: b_t + b of the matching dense layer
+  float* freqs = nullptr;   // [E/2]
+  float* gamma = nullptr;   // [n_gn, H]
+  float* beta = nullptr;
+  float* post_bias = nullptr;  // [64]
+  std::vector<PackedWeight> packed;
+  std::vector<GemmOp> program;
+
+  // workspaces
+  __half* xa = nullptr;            // [m_pad, 64] blocked hi/lo
+  std::vector<__half*> act;        // blocked hi/lo [m_pad, H]
+  float* eps = nullptr;            // [m_pad, 64]
+  std::vector<float*> act32;       // validation mode, lazily allocated [m_pad, H]
+  float* x32 = nullptr;            // [m_pad, D] scratch pose buffer
+  // bias tables
+  int table_steps = 0;
+  float* t999_dev = nullptr;
+  float* emb = nullptr;
+  float* temb = nullptr;
+  float* table = nullptr;  // [steps, L, H]
+  std::vector<void*> owned;
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(zedo_plan* p, T** ptr, size_t count) {
+  ZEDO_CUDA_TRY(cudaMalloc((void**)ptr, count * sizeof(T)));
+  ZEDO_CUDA_TRY(cudaMemset(*ptr, 0, count * sizeof(T)));
+  p->owned.push_back(*ptr);
+  return 0;
+}
+
+int upload(zedo_plan* p, float** dst, const float* src_host, size_t count) {
+  int rc = dev_alloc(p, dst, count);
+  if (rc) return rc;
+  ZEDO_CUDA_TRY(cudaMemcpy(*dst, src_host, count * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+struct TensorMap {
+  std::map<std::string, std::vector<float>> t;
+  const std::vector<float>* get(const std::string& k, size_t numel) const {
+    auto it = t.find(k);
+    if (it == t.end() || it->second.size() != numel) return nullptr;
+    return &it->second;
+  }
+};
+
+int ensure_tables(zedo_plan* p, int steps) {
+  if (steps <= p->table_steps) return 0;
+  // old buffers stay owned by the plan until destroy; schedules are rarely re-grown
+  int rc;
+  if ((rc = dev_alloc(p, &p->t999_dev, (size_t)steps))) return rc;
+  if ((rc = dev_alloc(p, &p->emb, (size_t)steps * p->E))) return rc;
+  if ((rc = dev_alloc(p, &p->temb, (size_t)steps * p->E))) return rc;
+  if ((rc = dev_alloc(p, &p->table, (size_t)steps * p->L * p->H))) return rc;
+  p->table_steps = steps;
+  return 0;
+}
+
+// table[s, l, :] = W_lt . SiLU(W_s emb(t999_s) + b_s) + b_lt + b_l      (model.py:253-259,265,273,281)
+int build_tables(zedo_plan* p, const float* t999_host, int steps, cudaStream_t st) {
+  int rc = ensure_tables(p, steps);
+  if (rc) return rc;
+  ZEDO_CUDA_TRY(cudaMemcpyAsync(p->t999_dev, t999_host, (size_t)steps * sizeof(float), cudaMemcpyHostToDevice, st));
+  if ((rc = launch_timestep_embedding(p->t999_dev, p->freqs, p->emb, steps, p->E / 2, st))) return rc;
+  if ((rc = launch_sgemm_tn(p->emb, p->E, p->Ws, p->E, p->bs, p->temb, p->E, steps, p->E, p->E, st))) return rc;
+  if ((rc = launch_silu_inplace(p->temb, (int64_t)steps * p->E, st))) return rc;
+  return launch_sgemm_tn(p->temb, p->E, p->Wt_cat, p->E, p->bt_cat, p->table, p->L * p->H, steps, p->L * p->H, p->E,
+                         st);
+}
+
+int ensure_act32(zedo_plan* p) {
+  if (!p->act32.empty()) return 0;
+  for (int i = 0; i < 3; ++i) {
+    float* b = nullptr;
+    int rc = dev_alloc(p, &b, (size_t)p->m_pad * p->H);
+    if (rc) return rc;
+    p->act32.push_back(b);
+  }
+  return 0;
+}
+
+// network forward for rows [0, B) of the pose buffer `x` (float32 [B, D]) using bias-table row
+// block `tbl` ([L, H]); result in p->eps (row stride 64).  When xa_ready the first operand was
+// already emitted by the geometry kernel.
+int net_forward(zedo_plan* p, const float* x, const float* tbl, int64_t B, int mode, bool xa_ready,
+                cudaStream_t st) {
+  int rc;
+  const int m_tiles = (int)((B + kActTileRows - 1) / kActTileRows);
+  if (mode == ZEDO_GEMM_FP32) {
+    if ((rc = ensure_act32(p))) return rc;
+    for (const GemmOp& op : p->program) {
+      const float* in = op.in_buf < 0 ? x : p->act32[op.in_buf];
+      const int K = p->w_k[op.weight], N = p->w_n[op.weight];
+      if (op.epi == EPI_LINEAR_F32) {
+        if ((rc = launch_sgemm_tn(in, K, p->w32[op.weight], K, p->post_bias, p->eps, 64, (int)B, N, K, st))) return rc;
+      } else {
+        float* raw = p->act32[2];
+        if ((rc = launch_sgemm_tn(in, K, p->w32[op.weight], K, nullptr, raw, p->H, (int)B, N, K, st))) return rc;
+        if ((rc = launch_gn_silu_rows(raw, tbl + (size_t)op.table_row * p->H, nullptr,
+                                      p->gamma + (size_t)op.gn * p->H, p->beta + (size_t)op.gn * p->H,
+                                      op.resid_buf >= 0 ? p->act32[op.resid_buf] : nullptr, p->act32[op.out_buf], B,
+                                      p->H, p->desc.gn_eps, st)))
+          return rc;
+      }
+    }
+    return 0;
+  }
+  if (mode != ZEDO_GEMM_SPLIT3 && mode != ZEDO_GEMM_FP16) return ZEDO_E_INVALID;
+  const int nprod = mode == ZEDO_GEMM_SPLIT3 ? 3 : 1;
+  if (!xa_ready && (rc = launch_pack_x(x, p->xa, B, p->D, st))) return rc;
+  for (const GemmOp& op : p->program) {
+    const PackedWeight& w = p->packed[op.weight];
+    LayerArgs a{};
+    a.A = op.in_buf < 0 ? p->xa : p->act[op.in_buf];
+    a.W = w.dev;
+    a.cbias = op.table_row >= 0 ? tbl + (size_t)op.table_row * p->H : p->post_bias;
+    a.gamma = op.gn >= 0 ? p->gamma + (size_t)op.gn * p->H : nullptr;
+    a.beta = op.gn >= 0 ? p->beta + (size_t)op.gn * p->H : nullptr;
+    a.addend = op.addend_buf >= 0 ? p->act[op.addend_buf] : nullptr;
+    a.resid = op.resid_buf >= 0 ? p->act[op.resid_buf] : nullptr;
+    a.out = op.out_buf >= 0 ? p->act[op.out_buf] : nullptr;
+    a.out_f32 = p->eps;
+    a.ld_out = 64;
+    a.m_tiles = m_tiles;
+    a.n_tiles = w.n_pad / w.bn;
+    a.num_kb = w.k_pad / kBlockK;
+    a.descale = w.descale;
+    a.gn_eps = p->desc.gn_eps;
+    if ((rc = launch_layer_tc(a, w.bn, nprod, op.epi, p->num_sms, st))) return rc;
+  }
+  return 0;
+}
+
+int check_batch(const zedo_plan* p, int64_t B) {
+  if (p == nullptr) return ZEDO_E_INVALID;
+  if (B < 0 || B > p->cap) return ZEDO_E_SHAPE;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int zedo_abi_version(void) { return ZEDO_B200_ABI_VERSION; }
+int64_t zedo_launch_count(void) { return g_launches.load(); }
+
+const char* zedo_strerror(int code) {
+  switch (code) {
+    case 0: return "ok";
+    case ZEDO_E_INVALID: return "zedo: invalid argument";
+    case ZEDO_E_SHAPE: return "zedo: unsupported shape or batch exceeds plan capacity";
+    case ZEDO_E_MISSING: return "zedo: state_dict tensor missing or wrong size";
+    case ZEDO_E_NOMEM: return "zedo: host allocation failed";
+    case ZEDO_E_STATE: return "zedo: invalid call order";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "zedo: unknown error";
+  }
+}
+
+int zedo_subvp_scalars(float t, float beta_min, float beta_max, float* beta_t, float* diffusion, float* std) {
+  const SdeCoef c = subvp_coef(t, beta_min, beta_max, 1000);
+  if (beta_t) *beta_t = c.beta_t;
+  if (diffusion) *diffusion = c.diffusion;
+  if (std) *std = c.std;
+  return 0;
+}
+
+int64_t zedo_blocked_offset(int64_t row, int64_t col, int64_t cols, int32_t tile_rows, int32_t hl) {
+  return blocked_half_offset(row, col, round_up(cols, kBlockK), tile_rows, hl) * 2;
+}
+
+int64_t zedo_plan_capacity(const zedo_plan* plan) { return plan ? plan->cap : 0; }
+
+int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tensors, const char* const* names,
+                     const float* const* tensors, const int64_t* numels, int64_t max_batch, int32_t device) {
+  if (!out || !desc || !names || !tensors || !numels) return ZEDO_E_INVALID;
+  *out = nullptr;
+  if (desc->kind != ZEDO_NET_SCORE_FC_ADV) return ZEDO_E_SHAPE;  // control net: see DESIGN.md (next)
+  const int D = desc->n_joints * 3, H = desc->hidden, E = desc->embed, NB = desc->n_blocks;
+  // GroupNorm(32, hidden): the fused epilogue normalises groups of exactly 32 contiguous channels,
+  // i.e. hidden == 1024 -- the only width the reference drivers instantiate (run/opt_main.py:35).
+  if (desc->n_joints < 1 || desc->n_joints > 21 || D > 64 || H != 1024 || E < 16 || E % 16 != 0 || NB < 1 ||
+      NB > 8 || max_batch < 1)
+    return ZEDO_E_SHAPE;
+  ZEDO_CUDA_TRY(cudaSetDevice(device));
+  zedo_plan* p = new (std::nothrow) zedo_plan();
+  if (!p) return ZEDO_E_NOMEM;
+  p->desc = *desc;
+  p->device = device;
+  p->D = D;
+  p->H = H;
+  p->E = E;
+  p->L = 1 + 2 * NB;
+  p->cap = max_batch;
+  p->m_pad = round_up(max_batch, kActTileRows);
+  int rc = 0;
+#define PLAN_TRY(expr)         \
+  do {                         \
+    rc = (expr);               \
+    if (rc) {                  \
+      zedo_plan_destroy(p);    \
+      return rc;               \
+    }                          \
+  } while (0)
+  {
+    int sms = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) PLAN_TRY((int)e);
+    p->num_sms = sms;
+  }
+  // gather the state_dict on the host (pointers may be host or device: cudaMemcpyDefault)
+  TensorMap tm;
+  for (int i = 0; i < n_tensors; ++i) {
+    std::string k = names[i] ? names[i] : "";
+    if (k.rfind("module.", 0) == 0) k = k.substr(7);
+    std::vector<float> v((size_t)numels[i]);
+    cudaError_t e = cudaMemcpy(v.data(), tensors[i], v.size() * sizeof(float), cudaMemcpyDefault);
+    if (e != cudaSuccess) PLAN_TRY((int)e);
+    tm.t[k] = std::move(v);
+  }
+  auto need = [&](const std::string& k, size_t n) -> const std::vector<float>* { return tm.get(k, n); };
+#define NEED(var, key, n)                \
+  const std::vector<float>* var = need(key, n); \
+  if (!var) PLAN_TRY(ZEDO_E_MISSING)
+
+  // dense layers in execution order + their time projections
+  std::vector<std::string> dense = {"pre_dense"};
+  std::vector<std::string> gnorm = {"pre_gnorm"};
+  for (int b = 1; b <= NB; ++b) {
+    dense.push_back("b" + std::to_string(b) + "_dense1");
+    dense.push_back("b" + std::to_string(b) + "_dense2");
+    gnorm.push_back("b" + std::to_string(b) + "_gnorm1");
+    gnorm.push_back("b" + std::to_string(b) + "_gnorm2");
+  }
+  std::vector<float> wt_cat((size_t)p->L * H * E), bt_cat((size_t)p->L * H), gam((size_t)p->L * H),
+      bet((size_t)p->L * H);
+  for (int l = 0; l < p->L; ++l) {
+    const int K = l == 0 ? D : H;
+    NEED(w, dense[l] + ".weight", (size_t)H * K);
+    NEED(b, dense[l] + ".bias", (size_t)H);
+    NEED(wt, dense[l] + "_t.weight", (size_t)H * E);
+    NEED(bt, dense[l] + "_t.bias", (size_t)H);
+    NEED(g, gnorm[l] + ".weight", (size_t)H);
+    NEED(be, gnorm[l] + ".bias", (size_t)H);
+    std::memcpy(&wt_cat[(size_t)l * H * E], wt->data(), (size_t)H * E * sizeof(float));
+    for (int i = 0; i < H; ++i) {
+      bt_cat[(size_t)l * H + i] = (*bt)[i] + (*b)[i];
+      gam[(size_t)l * H + i] = (*g)[i];
+      bet[(size_t)l * H + i] = (*be)[i];
+    }
+    PackedWeight pw;
+    PLAN_TRY(pack_weight(w->data(), H, K, 256, &pw));
+    p->owned.push_back(pw.dev);
+    p->packed.push_back(pw);
+    float* w32 = nullptr;
+    PLAN_TRY(upload(p, &w32, w->data(), w->size()));
+    p->w32.push_back(w32);
+    p->w_n.push_back(H);
+    p->w_k.push_back(K);
+  }
+  {
+    NEED(w, "post_dense.weight", (size_t)D * H);
+    NEED(b, "post_dense.bias", (size_t)D);
+    PackedWeight pw;
+    PLAN_TRY(pack_weight(w->data(), D, H, 64, &pw));
+    p->owned.push_back(pw.dev);
+    p->packed.push_back(pw);
+    float* w32 = nullptr;
+    PLAN_TRY(upload(p, &w32, w->data(), w->size()));
+    p->w32.push_back(w32);
+    p->w_n.push_back(D);
+    p->w_k.push_back(H);
+    std::vector<float> pb(64, 0.f);
+    for (int i = 0; i < D; ++i) pb[i] = (*b)[i];
+    PLAN_TRY(upload(p, &p->post_bias, pb.data(), pb.size()));
+  }
+  {
+    NEED(ws, "shared_time_embed.0.weight", (size_t)E * E);
+    NEED(bsv, "shared_time_embed.0.bias", (size_t)E);
+    PLAN_TRY(upload(p, &p->Ws, ws->data(), ws->size()));
+    PLAN_TRY(upload(p, &p->bs, bsv->data(), bsv->size()));
+  }
+  PLAN_TRY(upload(p, &p->Wt_cat, wt_cat.data(), wt_cat.size()));
+  PLAN_TRY(upload(p, &p->bt_cat, bt_cat.data(), bt_cat.size()));
+  PLAN_TRY(upload(p, &p->gamma, gam.data(), gam.size()));
+  PLAN_TRY(upload(p, &p->beta, bet.data(), bet.size()));
+  {
+    // emb = exp(arange(half) * -(log(10000) / (half - 1)))   (model.py:85-88), float32
+    const int half = E / 2;
+    std::vector<float> fr(half);
+    const float coef = (float)(-(std::log(10000.0) / (double)(half - 1)));
+    for (int k = 0; k < half; ++k) fr[k] = expf((float)k * coef);
+    PLAN_TRY(upload(p, &p->freqs, fr.data(), fr.size()));
+  }
+  // program: pre -> [dense1 -> dense2 (+residual)] x NB -> post; two ping-pong activation buffers
+  p->program.push_back({0, -1, 0, 0, 0, -1, -1, EPI_GN_SILU});
+  for (int b = 0; b < NB; ++b) {
+    p->program.push_back({1 + 2 * b, 0, 1, 1 + 2 * b, 1 + 2 * b, -1, -1, EPI_GN_SILU});
+    p->program.push_back({2 + 2 * b, 1, 0, 2 + 2 * b, 2 + 2 * b, 0, -1, EPI_GN_SILU});
+  }
+  p->program.push_back({p->L, 0, -1, -1, -1, -1, -1, EPI_LINEAR_F32});
+  // workspaces
+  PLAN_TRY(dev_alloc(p, &p->xa, (size_t)p->m_pad * kBlockK * 2));
+  for (int i = 0; i < 2; ++i) {
+    __half* a = nullptr;
+    PLAN_TRY(dev_alloc(p, &a, (size_t)p->m_pad * H * 2));
+    p->act.push_back(a);
+  }
+  PLAN_TRY(dev_alloc(p, &p->eps, (size_t)p->m_pad * 64));
+  PLAN_TRY(dev_alloc(p, &p->x32, (size_t)p->m_pad * D));
+  PLAN_TRY(ensure_tables(p, 1));
+  ZEDO_CUDA_TRY(cudaDeviceSynchronize());
+#undef NEED
+#undef PLAN_TRY
+  *out = p;
+  return 0;
+}
+
+int zedo_plan_destroy(zedo_plan* plan) {
+  if (!plan) return 0;
+  cudaSetDevice(plan->device);
+  cudaDeviceSynchronize();
+  for (void* q : plan->owned) cudaFree(q);
+  delete plan;
+  return 0;
+}
+
+int zedo_score_forward(zedo_plan* plan, const float* x, float t999, float* out, int64_t B, int32_t gemm_mode,
+                       void* stream) {
+  int rc = check_batch(plan, B);
+  if (rc) return rc;
+  if (!x || !out) return ZEDO_E_INVALID;
+  if (B == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = build_tables(plan, &t999, 1, st))) return rc;
+  if ((rc = net_forward(plan, x, plan->table, B, gemm_mode, false, st))) return rc;
+  ZEDO_CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)plan->D * sizeof(float), plan->eps, 64 * sizeof(float),
+                                  (size_t)plan->D * sizeof(float), (size_t)B, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int zedo_grad_field(const float* uv, const float* x, const float* K, float* conf, float* T, int32_t solve_T,
+                    int32_t clamp_conf_inplace, float* g, float* x_out, int64_t B, int32_t J, void* stream) {
+  if (!uv || !x || !K || !T) return ZEDO_E_INVALID;
+  if (J < 1 || J > 32 || B < 0) return ZEDO_E_SHAPE;
+  return launch_grad_field(uv, x, K, conf, T, solve_T, clamp_conf_inplace, g, x_out, nullptr, B, J,
+                           (cudaStream_t)stream);
+}
+
+int zedo_sde_step(zedo_plan* plan, const float* x, float t, const float* z, int32_t predictor,
+                  int32_t probability_flow, float beta_min, float beta_max, int32_t n_scales, float* x_next,
+                  float* x_mean, int64_t B, int32_t gemm_mode, void* stream) {
+  int rc = check_batch(plan, B);
+  if (rc) return rc;
+  if (!x || n_scales < 1) return ZEDO_E_INVALID;
+  if (predictor != ZEDO_PRED_EULER_MARUYAMA && predictor != ZEDO_PRED_REVERSE_DIFFUSION) return ZEDO_E_INVALID;
+  if (B == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float t999 = t * 999.0f;  // labels = t * 999 (utils.py:762)
+  if ((rc = build_tables(plan, &t999, 1, st))) return rc;
+  if ((rc = net_forward(plan, x, plan->table, B, gemm_mode, false, st))) return rc;
+  const SdeCoef c = subvp_coef(t, beta_min, beta_max, n_scales);
+  return launch_sde_update(x, plan->eps, 64, z, c, predictor, probability_flow, x_next, x_mean, B, plan->D, st);
+}
+
+int zedo_oil_loop(zedo_plan* plan, float* x, float* T, const float* uv, const float* K, float* conf,
+                  const float* t_sched, int32_t steps, int32_t phase_switch, float beta_min, float beta_max,
+                  int32_t n_scales, float* dump, const int32_t* dump_steps, int32_t n_dump, int64_t B,
+                  int32_t gemm_mode, void* stream) {
+  int rc = check_batch(plan, B);
+  if (rc) return rc;
+  if (!x || !T || !uv || !K || !t_sched || steps < 0 || n_scales < 1) return ZEDO_E_INVALID;
+  if (n_dump > 0 && (!dump || !dump_steps)) return ZEDO_E_INVALID;
+  if (B == 0 || steps == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int J = plan->desc.n_joints, D = plan->D;
+  std::vector<float> t999((size_t)steps);
+  for (int i = 0; i < steps; ++i) t999[i] = t_sched[i] * 999.0f;
+  if ((rc = build_tables(plan, t999.data(), steps, st))) return rc;
+  // the pageable t999 buffer has been consumed by the (staged) async copy once the call returns
+  const bool tc = gemm_mode != ZEDO_GEMM_FP32;
+  int next_dump = 0;
+  for (int i = 0; i < steps; ++i) {
+    // gradient_field_gen + `denoise_x += joint_gradient` (opt_main.py:203-208); conf is clamped in
+    // place by the first call of the reference and stays clamped
+    if ((rc = launch_grad_field(uv, x, K, conf, T, i >= phase_switch ? 1 : 0, i == 0 ? 1 : 0, nullptr, x,
+                                tc ? plan->xa : nullptr, B, J, st)))
+      return rc;
+    const float* tbl = plan->table + (size_t)i * plan->L * plan->H;
+    if ((rc = net_forward(plan, x, tbl, B, gemm_mode, tc, st))) return rc;
+    const SdeCoef c = subvp_coef(t_sched[i], beta_min, beta_max, n_scales);
+    // pc_sampler with probability_flow=True, noise_removal=True returns x_mean (sampling.py:524-527)
+    if ((rc = launch_sde_update(x, plan->eps, 64, nullptr, c, ZEDO_PRED_EULER_MARUYAMA, 1, nullptr, x, B, D, st)))
+      return rc;
+    while (next_dump < n_dump && dump_steps[next_dump] == i) {
+      ZEDO_CUDA_TRY(cudaMemcpyAsync(dump + (size_t)next_dump * B * D, x, (size_t)B * D * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, st));
+      ++next_dump;
+    }
+  }
+  return 0;
+}
+
+int zedo_ipo_fit(const float* x0, const float* uv, const float* K, const int32_t* keylist, int32_t nkey,
+                 int32_t axes_mask, float ipo_T, float minT, float maxT, int32_t iters, int64_t B_global, float lr,
+                 float* R, float* T, float* x_rot, float* qs, int64_t B, int32_t J, void* stream) {
+  if (!x0 || !uv || !K || !keylist || !R || !T) return ZEDO_E_INVALID;
+  if (nkey < 1 || nkey > 32 || J < 1 || J > 64 || iters < 0 || iters > 4096 || B < 0 || B_global < 1)
+    return ZEDO_E_SHAPE;
+  for (int i = 0; i < nkey; ++i)
+    if (keylist[i] < 0 || keylist[i] >= J) return ZEDO_E_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  int* kl = nullptr;
+  ZEDO_CUDA_TRY(cudaMallocAsync((void**)&kl, (size_t)nkey * sizeof(int), st));
+  ZEDO_CUDA_TRY(cudaMemcpyAsync(kl, keylist, (size_t)nkey * sizeof(int), cudaMemcpyHostToDevice, st));
+  int rc = launch_ipo_fit(x0, uv, K, kl, nkey, axes_mask, ipo_T, minT, maxT, iters, B_global, lr, R, T, x_rot, qs, B,
+                          J, st);
+  cudaFreeAsync(kl, st);
+  return rc;
+}
+
+int zedo_rotopt_forward(const float* q, const float* scale, const float* xk, const float* T0, const float* K,
+                        float minT, float maxT, float* uv_out, int64_t B, int32_t nk, void* stream) {
+  if (!q || !scale || !xk || !T0 || !K || !uv_out) return ZEDO_E_INVALID;
+  if (nk < 1 || B < 0) return ZEDO_E_SHAPE;
+  return launch_rotopt_forward(q, scale, xk, T0, K, minT, maxT, uv_out, B, nk, (cudaStream_t)stream);
+}
+
+int zedo_rotopt_backward(const float* q, const float* scale, const float* xk, const float* T0, const float* K,
+                         float minT, float maxT, const float* d_uv, float* d_q, float* d_scale, int64_t B,
+                         int32_t nk, void* stream) {
+  if (!q || !scale || !xk || !T0 || !K || !d_uv || !d_q || !d_scale) return ZEDO_E_INVALID;
+  if (nk < 1 || nk > 32 || B < 0) return ZEDO_E_SHAPE;
+  return launch_rotopt_backward(q, scale, xk, T0, K, minT, maxT, d_uv, d_q, d_scale, B, nk, (cudaStream_t)stream);
+}
+
+int zedo_eval_multi(const float* pred, const double* gt, int32_t protocol2, int64_t N, int32_t S, int32_t J,
+                    const int32_t* joint_subset, int32_t n_sub, double* err_min, int32_t* argmin, double* err_all,
+                    void* stream) {
+  if (!pred || !gt || !err_min || !argmin) return ZEDO_E_INVALID;
+  if (J < 1 || J > 32 || S < 1 || N < 0) return ZEDO_E_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  int* sub = nullptr;
+  if (joint_subset != nullptr) {
+    if (n_sub < 1 || n_sub > J) return ZEDO_E_SHAPE;
+    ZEDO_CUDA_TRY(cudaMallocAsync((void**)&sub, (size_t)n_sub * sizeof(int), st));
+    ZEDO_CUDA_TRY(cudaMemcpyAsync(sub, joint_subset, (size_t)n_sub * sizeof(int), cudaMemcpyHostToDevice, st));
+  }
+  int rc = launch_eval_multi(pred, gt, protocol2, N, S, J, sub, n_sub, err_min, argmin, err_all, st);
+  if (sub) cudaFreeAsync(sub, st);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+// Shared helpers for the ZeDO B200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "../../include/zedo_b200.h"
+
+namespace zedo {
+
+// ---- launch accounting (zedo_launch_count) -----------------------------------------------------
+void count_launch(int n = 1);
+
+#define ZEDO_CUDA_TRY(expr)                        \
+  do {                                             \
+    cudaError_t _e = (expr);                       \
+    if (_e != cudaSuccess) return (int)_e;         \
+  } while (0)
+
+#define ZEDO_LAUNCH_CHECK()                        \
+  do {                                             \
+    ::zedo::count_launch();                        \
+    cudaError_t _e = cudaGetLastError();           \
+    if (_e != cudaSuccess) return (int)_e;         \
+  } while (0)
+
+// ---- blocked, 128B-swizzled fp16 operand layout -------------------------------------------------
+// A [rows, cols] fp16 operand (cols padded to a multiple of 64) is stored as tiles of
+// TILE_ROWS x 64 halves; tile (rt, kb) has a "hi" image followed by a "lo" image, each
+// TILE_ROWS*128 bytes.  Inside an image row r occupies bytes [r*128, r*128+128) and its eight
+// 16-byte chunks are permuted c -> c ^ (r & 7): exactly the shared-memory image a TMA
+// SWIZZLE_128B box {64, TILE_ROWS} would produce, so one linear bulk copy (cp.async.bulk)
+// of the tile is directly consumable by tcgen05.mma with a K-major SWIZZLE_128B descriptor.
+constexpr int kBlockK = 64;        // halves per tile row (128 bytes)
+constexpr int kActTileRows = 128;  // BLOCK_M
+
+__host__ __device__ inline int64_t blocked_half_offset(int64_t row, int64_t col, int64_t cols_padded,
+                                                       int tile_rows, int hl) {
+  const int64_t num_kb = cols_padded / kBlockK;
+  const int64_t rt = row / tile_rows, r = row % tile_rows;
+  const int64_t kb = col / kBlockK, c = col % kBlockK;
+  const int64_t chunk = (c >> 3) ^ (r & 7);
+  const int64_t image = (int64_t)tile_rows * kBlockK;  // halves per hi or lo image
+  return ((rt * num_kb + kb) * 2 + hl) * image + r * kBlockK + chunk * 8 + (c & 7);
+}
+
+__host__ __device__ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// ---- hi/lo split --------------------------------------------------------------------------------
+__device__ __forceinline__ void split_hi_lo(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+
+__device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- small 3x3 helpers (row-major) ----------------------------------------------------------------
+__device__ __forceinline__ void inv3x3(const float* m, float* o) {
+  const float a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+  const float A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
+  const float det = a * A + b * B + c * C;
+  const float r = 1.0f / det;
+  o[0] = A * r;
+  o[1] = -(b * i - c * h) * r;
+  o[2] = (b * f - c * e) * r;
+  o[3] = B * r;
+  o[4] = (a * i - c * g) * r;
+  o[5] = -(a * f - c * d) * r;
+  o[6] = C * r;
+  o[7] = -(a * h - b * g) * r;
+  o[8] = (a * e - b * d) * r;
+}
+
+// sub-VP scalars of one step, float32 op order of sde_lib.py:187-198 / utils.py:762-776
+struct SdeCoef {
+  float beta_t;     // beta(t)
+  float diffusion;  // g(t)
+  float std;        // marginal std (1 - exp(2 lmc))
+  float dt;         // -1/N (Euler-Maruyama) ; +1/N for the reverse-diffusion discretisation
+};
+SdeCoef subvp_coef(float t, float beta_min, float beta_max, int n_scales);
+
+}  // namespace zedo

@@ -1,0 +1,147 @@
+// K5: multi-hypothesis evaluation -- MPJPE / PA-MPJPE and the per-pose argmin over hypotheses.
+//
+// Restates eval_multi (lib/dataset/h36m.py:394-417, pw3d.py:303-338) and align_to_gt / procrustes
+// (lib/utils/transforms.py:42-148: scaling=True, reflection='best', i.e. NO determinant fix, so
+// reflections are allowed).  One warp per pose, lane j owns joint j, the S hypotheses are a serial
+// loop so "first minimum wins" exactly like np.argmin.  Float64 throughout: the reference's
+// numpy path promotes to float64 (gt comes from a float64 pickle), and the selection indices
+// have to be bit-exact.
+#include "kernels.cuh"
+
+namespace zedo {
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One-sided Jacobi SVD of a 3x3 matrix M (row-major): on exit the columns of M are U_i * s_i and
+// V accumulates the right rotations, M_in = U diag(s) V^T.
+__device__ void svd3x3_onesided(double* M, double* V) {
+  V[0] = V[4] = V[8] = 1.0;
+  V[1] = V[2] = V[3] = V[5] = V[6] = V[7] = 0.0;
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0;
+#pragma unroll
+    for (int pair = 0; pair < 3; ++pair) {
+      const int p = pair == 2 ? 1 : 0;
+      const int q = pair == 0 ? 1 : 2;
+      const double alpha = M[p] * M[p] + M[3 + p] * M[3 + p] + M[6 + p] * M[6 + p];
+      const double beta = M[q] * M[q] + M[3 + q] * M[3 + q] + M[6 + q] * M[6 + q];
+      const double gamma = M[p] * M[q] + M[3 + p] * M[3 + q] + M[6 + p] * M[6 + q];
+      off = fmax(off, fabs(gamma) / sqrt(fmax(alpha * beta, 1e-300)));
+      if (fabs(gamma) <= 1e-300) continue;
+      const double zeta = (beta - alpha) / (2.0 * gamma);
+      const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+      const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const double mp = M[3 * r + p], mq = M[3 * r + q];
+        M[3 * r + p] = c * mp - s * mq;
+        M[3 * r + q] = s * mp + c * mq;
+        const double vp = V[3 * r + p], vq = V[3 * r + q];
+        V[3 * r + p] = c * vp - s * vq;
+        V[3 * r + q] = s * vp + c * vq;
+      }
+    }
+    if (off < 1e-15) break;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+eval_multi_kernel(const float* __restrict__ pred, const double* __restrict__ gt, int protocol2, int64_t N, int S,
+                  int J, const int* __restrict__ subset, int n_sub, double* __restrict__ err_min,
+                  int* __restrict__ argmin, double* __restrict__ err_all) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const bool active = lane < J;
+  // joints that count in the mean: all J, or the listed subset (e.g. the 12 SyRIP joints)
+  bool counted = active;
+  int n_counted = J;
+  if (subset != nullptr) {
+    counted = false;
+    for (int i = 0; i < n_sub; ++i) counted |= (subset[i] == lane);
+    n_counted = n_sub;
+  }
+  double g0 = 0, g1 = 0, g2 = 0;
+  if (active) {
+    g0 = gt[(n * J + lane) * 3 + 0];
+    g1 = gt[(n * J + lane) * 3 + 1];
+    g2 = gt[(n * J + lane) * 3 + 2];
+  }
+  // gt statistics for Procrustes (transforms.py:74-85)
+  const double invJ = 1.0 / J;
+  const double am0 = warp_sum_d(g0) * invJ, am1 = warp_sum_d(g1) * invJ, am2 = warp_sum_d(g2) * invJ;
+  const double a0 = active ? g0 - am0 : 0, a1 = active ? g1 - am1 : 0, a2 = active ? g2 - am2 : 0;
+  const double a_norm = sqrt(warp_sum_d(a0 * a0 + a1 * a1 + a2 * a2));
+
+  double best = 0.0;
+  int best_idx = 0;
+  for (int s = 0; s < S; ++s) {
+    double p0 = 0, p1 = 0, p2 = 0;
+    if (active) {
+      const float* pp = pred + ((n * S + s) * J + lane) * 3;
+      p0 = pp[0];
+      p1 = pp[1];
+      p2 = pp[2];
+    }
+    if (protocol2) {
+      const double bm0 = warp_sum_d(p0) * invJ, bm1 = warp_sum_d(p1) * invJ, bm2 = warp_sum_d(p2) * invJ;
+      double b0 = active ? p0 - bm0 : 0, b1 = active ? p1 - bm1 : 0, b2 = active ? p2 - bm2 : 0;
+      const double b_norm = sqrt(warp_sum_d(b0 * b0 + b1 * b1 + b2 * b2));
+      const double an0 = a0 / a_norm, an1 = a1 / a_norm, an2 = a2 / a_norm;
+      b0 /= b_norm;
+      b1 /= b_norm;
+      b2 /= b_norm;
+      double M[9], V[9];  // M = A0^T B0
+      M[0] = warp_sum_d(an0 * b0); M[1] = warp_sum_d(an0 * b1); M[2] = warp_sum_d(an0 * b2);
+      M[3] = warp_sum_d(an1 * b0); M[4] = warp_sum_d(an1 * b1); M[5] = warp_sum_d(an1 * b2);
+      M[6] = warp_sum_d(an2 * b0); M[7] = warp_sum_d(an2 * b1); M[8] = warp_sum_d(an2 * b2);
+      svd3x3_onesided(M, V);
+      // R = V U^T = sum_i v_i u_i^T with u_i = M[:, i] / s_i ; trace(S) = sum_i s_i
+      double Rm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      double tr = 0.0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double si = sqrt(M[i] * M[i] + M[3 + i] * M[3 + i] + M[6 + i] * M[6 + i]);
+        tr += si;
+        const double inv = si > 0.0 ? 1.0 / si : 0.0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) Rm[3 * r + c] += V[3 * r + i] * (M[3 * c + i] * inv);
+      }
+      const double k = a_norm * tr;  // Z = A_norm * trace * (B0 R) + A_bar   (transforms.py:113)
+      p0 = k * (b0 * Rm[0] + b1 * Rm[3] + b2 * Rm[6]) + am0;
+      p1 = k * (b0 * Rm[1] + b1 * Rm[4] + b2 * Rm[7]) + am1;
+      p2 = k * (b0 * Rm[2] + b1 * Rm[5] + b2 * Rm[8]) + am2;
+    }
+    const double d0 = p0 - g0, d1 = p1 - g1, d2 = p2 - g2;
+    const double e = counted ? sqrt(d0 * d0 + d1 * d1 + d2 * d2) : 0.0;
+    const double err = warp_sum_d(e) / n_counted;
+    if (err_all != nullptr && lane == 0) err_all[n * S + s] = err;
+    if (s == 0 || err < best) {
+      best = err;
+      best_idx = s;
+    }
+  }
+  if (lane == 0) {
+    err_min[n] = best;
+    argmin[n] = best_idx;
+  }
+}
+
+int launch_eval_multi(const float* pred, const double* gt, int protocol2, int64_t N, int S, int J,
+                      const int* subset_dev, int n_sub, double* err_min, int* argmin, double* err_all,
+                      cudaStream_t st) {
+  if (N == 0) return 0;
+  const int warps = 4;
+  eval_multi_kernel<<<(unsigned)((N + warps - 1) / warps), warps * 32, 0, st>>>(pred, gt, protocol2, N, S, J, subset_dev,
+                                                                             n_sub, err_min, argmin, err_all);
+  ZEDO_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace zedo

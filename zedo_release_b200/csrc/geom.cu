@@ -1,0 +1,243 @@
+// K3 / K2: per-step reprojection fit (one warp per pose) and the fused SDE predictor update.
+//
+// grad_field_kernel restates gradient_field_gen (reference simple_zeroshot_opt.py:46-125):
+//   rays r_j = K^-1 [u_j, v_j, 1], r_j /= r_j.z                                     (:61-71)
+//   optional least-squares translation, rows weighted conf^2, sign flip on T_z < 0   (:73-93)
+//   r^_j = r_j/|r_j|; p_j = X_j + T; g_j = (p_j . r^_j) r^_j - p_j                   (:33-36,99,109)
+// Lane j of the warp owns joint j (J <= 32); the seven normal-equation sums are xor-shuffle
+// reductions, so every lane holds the same T.  The kernel is HBM-bound: per pose it moves
+// x (r/w), uv, conf, K, T = 672 bytes at J = 17 and (optionally) emits the first GEMM's
+// fp16 hi/lo operand in the blocked swizzled layout.
+#include "kernels.cuh"
+
+namespace zedo {
+
+constexpr int kGeomWarps = 8;
+
+__global__ void __launch_bounds__(kGeomWarps * 32)
+grad_field_kernel(const float* __restrict__ uv, const float* x, const float* __restrict__ Kmat,
+                  float* conf, float* T, int solve_T, int clamp_inplace, float* g_out, float* x_out,
+                  __half* __restrict__ xa, int64_t B, int J) {
+  __shared__ float stage[kGeomWarps][kBlockK];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int64_t pose = (int64_t)blockIdx.x * kGeomWarps + wib;
+  if (pose >= B) return;
+  const bool active = lane < J;
+
+  // intrinsics: lanes 0..8 load one entry each, broadcast, invert (general 3x3: skew allowed)
+  float kv = lane < 9 ? Kmat[pose * 9 + lane] : 0.f;
+  float Km[9], Ki[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Km[i] = __shfl_sync(0xffffffffu, kv, i);
+  inv3x3(Km, Ki);
+
+  float u = 0.f, v = 0.f, X0 = 0.f, X1 = 0.f, X2 = 0.f, c = 1.f;
+  if (active) {
+    const float2 p2 = *reinterpret_cast<const float2*>(uv + (pose * J + lane) * 2);
+    u = p2.x;
+    v = p2.y;
+    const float* xp = x + (pose * J + lane) * 3;
+    X0 = xp[0];
+    X1 = xp[1];
+    X2 = xp[2];
+    if (conf != nullptr) {
+      c = conf[pose * J + lane];
+      if (c > 1.f) c = 1.f;          // conf[conf > 1] = 1        (:65)
+      if (c < 1e-4f) c = 1e-4f;      // conf[conf < 1e-4] = 1e-4  (:66)
+      if (clamp_inplace) conf[pose * J + lane] = c;
+    }
+  }
+  float rx = Ki[0] * u + Ki[1] * v + Ki[2];
+  float ry = Ki[3] * u + Ki[4] * v + Ki[5];
+  float rz = Ki[6] * u + Ki[7] * v + Ki[8];
+  rx = rx / rz;
+  ry = ry / rz;
+  rz = rz / rz;
+
+  float T0, T1, T2;
+  if (solve_T) {
+    const float w = active ? c * c : 0.f;  // row weight conf*conf on A and on b  (:85-88)
+    const float bx = (X0 - X2 * rx) * w, by = (X1 - X2 * ry) * w;
+    const float ax = rx * w, ay = ry * w, am = -w;
+    float S = warp_sum(am * am);
+    float Sxz = warp_sum(am * ax);
+    float Syz = warp_sum(am * ay);
+    float Szz = warp_sum(ax * ax + ay * ay);
+    float b0 = warp_sum(am * bx);
+    float b1 = warp_sum(am * by);
+    float b2 = warp_sum(ax * bx + ay * by);
+    float M[9] = {S, 0.f, Sxz, 0.f, S, Syz, Sxz, Syz, Szz};
+    float Mi[9];
+    inv3x3(M, Mi);
+    T0 = Mi[0] * b0 + Mi[1] * b1 + Mi[2] * b2;
+    T1 = Mi[3] * b0 + Mi[4] * b1 + Mi[5] * b2;
+    T2 = Mi[6] * b0 + Mi[7] * b1 + Mi[8] * b2;
+    if (T2 < 0.f) {  // T[T_z < 0] *= -1  (:93)
+      T0 = -T0;
+      T1 = -T1;
+      T2 = -T2;
+    }
+    if (lane == 0) {
+      T[pose * 3 + 0] = T0;
+      T[pose * 3 + 1] = T1;
+      T[pose * 3 + 2] = T2;
+    }
+  } else {
+    float tv = lane < 3 ? T[pose * 3 + lane] : 0.f;
+    T0 = __shfl_sync(0xffffffffu, tv, 0);
+    T1 = __shfl_sync(0xffffffffu, tv, 1);
+    T2 = __shfl_sync(0xffffffffu, tv, 2);
+  }
+
+  const float nrm = sqrtf(rx * rx + ry * ry + rz * rz);
+  const float hx = rx / nrm, hy = ry / nrm, hz = rz / nrm;
+  const float p0 = X0 + T0, p1 = X1 + T1, p2 = X2 + T2;
+  const float d = p0 * hx + p1 * hy + p2 * hz;
+  const float g0 = d * hx - p0, g1 = d * hy - p1, g2 = d * hz - p2;
+  const float n0 = X0 + g0, n1 = X1 + g1, n2 = X2 + g2;
+  if (active) {
+    const int64_t o = (pose * J + lane) * 3;
+    if (g_out != nullptr) {
+      g_out[o] = g0;
+      g_out[o + 1] = g1;
+      g_out[o + 2] = g2;
+    }
+    if (x_out != nullptr) {
+      x_out[o] = n0;
+      x_out[o + 1] = n1;
+      x_out[o + 2] = n2;
+    }
+  }
+  if (xa != nullptr) {
+    // emit row `pose` of the first GEMM's A operand: 64 halves (3J padded with zeros), hi and lo
+    float* st = stage[wib];
+    st[lane] = 0.f;
+    st[lane + 32] = 0.f;
+    __syncwarp();
+    if (active) {
+      st[lane * 3 + 0] = n0;
+      st[lane * 3 + 1] = n1;
+      st[lane * 3 + 2] = n2;
+    }
+    __syncwarp();
+    if (lane < 8) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        __half h0, l0, h1, l1;
+        split_hi_lo(st[lane * 8 + 2 * e], h0, l0);
+        split_hi_lo(st[lane * 8 + 2 * e + 1], h1, l1);
+        hi[e] = pack_half2(h0, h1);
+        lo[e] = pack_half2(l0, l1);
+      }
+      const int64_t oh = blocked_half_offset(pose, lane * 8, kBlockK, kActTileRows, 0);
+      const int64_t ol = blocked_half_offset(pose, lane * 8, kBlockK, kActTileRows, 1);
+      *reinterpret_cast<uint4*>(xa + oh) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(xa + ol) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
+// x [B, D] float32 -> blocked hi/lo A operand of the first GEMM (one k-block of 64 columns)
+__global__ void pack_x_kernel(const float* __restrict__ x, __half* __restrict__ xa, int64_t B, int D) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = t >> 3;
+  const int chunk = (int)(t & 7);
+  if (row >= B) return;
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c0 = chunk * 8 + 2 * e;
+    const float a = c0 < D ? x[row * D + c0] : 0.f;
+    const float b = c0 + 1 < D ? x[row * D + c0 + 1] : 0.f;
+    __half h0, l0, h1, l1;
+    split_hi_lo(a, h0, l0);
+    split_hi_lo(b, h1, l1);
+    hi[e] = pack_half2(h0, h1);
+    lo[e] = pack_half2(l0, l1);
+  }
+  *reinterpret_cast<uint4*>(xa + blocked_half_offset(row, chunk * 8, kBlockK, kActTileRows, 0)) =
+      make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(xa + blocked_half_offset(row, chunk * 8, kBlockK, kActTileRows, 1)) =
+      make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// K2: the predictor update, elementwise over [B, D]; eps is the network output with row
+// stride ld_eps.  Float32 op order of sampling.py:185-191 / sde_lib.py:93-107 / utils.py:762-776:
+//   score = -eps/std
+//   Euler-Maruyama:     drift = (-0.5 beta) x - g^2 score ; x_mean = x + drift*dt ; x = x_mean + (g sqrt(-dt)) z
+//   reverse diffusion:  f = (-0.5 beta) x * dt' ; rev_f = f - G^2 score ; x_mean = x - rev_f ; x = x_mean + G z
+__global__ void sde_update_kernel(const float* __restrict__ x, const float* __restrict__ eps, int ld_eps,
+                                  const float* __restrict__ z, float neg_half_beta, float g2, float std,
+                                  float dt, float noise_scale, int predictor, float* x_next, float* x_mean,
+                                  int64_t B, int D) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * D) return;
+  const int64_t row = idx / D;
+  const int e = (int)(idx - row * D);
+  const float xv = x[idx];
+  const float score = -eps[row * ld_eps + e] / std;
+  float xm;
+  if (predictor == ZEDO_PRED_EULER_MARUYAMA) {
+    const float drift = neg_half_beta * xv - g2 * score;
+    xm = xv + drift * dt;
+  } else {
+    const float f = neg_half_beta * xv * dt;
+    const float rev_f = f - g2 * score;
+    xm = xv - rev_f;
+  }
+  if (x_mean != nullptr) x_mean[idx] = xm;
+  if (x_next != nullptr) {
+    float xn = xm;
+    if (z != nullptr && noise_scale != 0.f) xn = xm + noise_scale * z[idx];
+    x_next[idx] = xn;
+  }
+}
+
+// ---- host launchers ---------------------------------------------------------------------------------
+
+int launch_grad_field(const float* uv, const float* x, const float* K, float* conf, float* T, int solve_T,
+                      int clamp_inplace, float* g, float* x_out, __half* xa, int64_t B, int J,
+                      cudaStream_t st) {
+  if (B == 0) return 0;
+  const int64_t blocks = (B + kGeomWarps - 1) / kGeomWarps;
+  grad_field_kernel<<<(unsigned)blocks, kGeomWarps * 32, 0, st>>>(uv, x, K, conf, T, solve_T, clamp_inplace, g,
+                                                                  x_out, xa, B, J);
+  ZEDO_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_pack_x(const float* x, __half* xa, int64_t B, int D, cudaStream_t st) {
+  if (B == 0) return 0;
+  const int64_t threads = B * 8;
+  pack_x_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, xa, B, D);
+  ZEDO_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_sde_update(const float* x, const float* eps, int ld_eps, const float* z, const SdeCoef& c,
+                      int predictor, int probability_flow, float* x_next, float* x_mean, int64_t B, int D,
+                      cudaStream_t st) {
+  if (B == 0) return 0;
+  float g2, dt, noise_scale;
+  if (predictor == ZEDO_PRED_EULER_MARUYAMA) {
+    g2 = c.diffusion * c.diffusion;
+    dt = c.dt;
+    // diffusion[:, None, None] * np.sqrt(-dt): float32 tensor times a python double scalar
+    noise_scale = probability_flow ? 0.f : c.diffusion * (float)sqrt(-(double)c.dt);
+  } else {
+    const float dtp = -c.dt;  // 1/N
+    const float G = c.diffusion * sqrtf(dtp);
+    g2 = G * G;
+    dt = dtp;
+    noise_scale = probability_flow ? 0.f : G;
+  }
+  const int64_t n = B * D;
+  sde_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, eps, ld_eps, z, -0.5f * c.beta_t, g2, c.std,
+                                                                 dt, noise_scale, predictor, x_next, x_mean, B, D);
+  ZEDO_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace zedo

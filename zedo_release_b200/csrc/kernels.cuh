@@ -1,0 +1,50 @@
+// Declarations shared between the kernel translation units and the C-ABI glue (api.cu).
+#pragma once
+#include "common.cuh"
+
+namespace zedo {
+
+struct LayerArgs {
+  const __half* A;
+  const __half* W;
+  const float* cbias;
+  const float* gamma;
+  const float* beta;
+  const __half* addend;
+  const __half* resid;
+  __half* out;
+  float* out_f32;
+  int ld_out;
+  int m_tiles, n_tiles, num_kb;
+  float descale;
+  float gn_eps;
+};
+constexpr int EPI_GN_SILU = 0, EPI_LINEAR_ACT = 1, EPI_LINEAR_F32 = 2;
+int launch_layer_tc(const LayerArgs& a, int bn, int nprod, int epi, int num_sms, cudaStream_t st);
+int launch_grad_field(const float* uv, const float* x, const float* K, float* conf, float* T, int solve_T,
+                      int clamp_inplace, float* g, float* x_out, __half* xa, int64_t B, int J, cudaStream_t st);
+int launch_pack_x(const float* x, __half* xa, int64_t B, int D, cudaStream_t st);
+int launch_sde_update(const float* x, const float* eps, int ld_eps, const float* z, const SdeCoef& c, int predictor,
+                      int probability_flow, float* x_next, float* x_mean, int64_t B, int D, cudaStream_t st);
+int launch_sgemm_tn(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M,
+                    int N, int K, cudaStream_t st);
+int launch_timestep_embedding(const float* t999, const float* freqs, float* emb, int n_steps, int half,
+                              cudaStream_t st);
+int launch_silu_inplace(float* v, int64_t n, cudaStream_t st);
+int launch_gn_silu_rows(const float* in, const float* cbias, const float* addend, const float* gamma,
+                        const float* beta, const float* resid, float* out, int64_t M, int C, float eps,
+                        cudaStream_t st);
+int launch_ipo_fit(const float* x0, const float* uv, const float* K, const int* keylist_dev, int nk, int axes_mask,
+                   float ipo_T, float minT, float maxT, int iters, int64_t B_global, float lr, float* R, float* T,
+                   float* x_rot, float* qs, int64_t B, int J, cudaStream_t st);
+int launch_rotopt_forward(const float* q, const float* scale, const float* xk, const float* T0, const float* K,
+                          float minT, float maxT, float* uv_out, int64_t B, int nk, cudaStream_t st);
+int launch_rotopt_backward(const float* q, const float* scale, const float* xk, const float* T0, const float* K,
+                           float minT, float maxT, const float* d_uv, float* d_q, float* d_scale, int64_t B, int nk,
+                           cudaStream_t st);
+int launch_eval_multi(const float* pred, const double* gt, int protocol2, int64_t N, int S, int J,
+                      const int* subset_dev, int n_sub, double* err_min, int* argmin, double* err_all,
+                      cudaStream_t st);
+
+
+}  // namespace zedo

@@ -1,0 +1,251 @@
+"""Host side of the B200 ZeDO hot path: torch tensors in, C-ABI calls out.
+
+PyTorch is only plumbing here (device memory, streams, ``torch.distributed``); every
+arithmetic operation of the path runs in the hand-written sm_100a kernels behind
+``libzedo_b200.so``.  Function-level citations are to the reference tree.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+GEMM_MODES = {"split3": nat.GEMM_SPLIT3, "fp16": nat.GEMM_FP16, "fp32": nat.GEMM_FP32}
+
+
+def _mode(mode) -> int:
+    return GEMM_MODES[mode] if isinstance(mode, str) else int(mode)
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (zedo_release_b200 has no CPU path)")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.contiguous().float()
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def linspace_schedule(t_start: float, eps: float, steps: int) -> np.ndarray:
+    """``torch.linspace(sde.T, sampling_eps, steps)`` in float32 (run/opt_main.py:197-198)."""
+    return torch.linspace(t_start, eps, steps, dtype=torch.float32).numpy()
+
+
+class ScorePlan:
+    """Packed score network + workspaces on one GPU (``zedo_plan``).
+
+    Replaces ``ScoreModelFC_Adv(...).to(device)`` + ``load_state_dict`` (run/opt_main.py:69-137)
+    for the hot path.  ``state`` maps the reference's state_dict names to float32 tensors.
+    """
+
+    def __init__(self, state: Dict[str, "torch.Tensor | np.ndarray"], n_joints: int = 17, hidden: int = 1024,
+                 embed: int = 512, n_blocks: int = 2, max_batch: int = 1024, device: Optional[int] = None,
+                 kind: int = nat.NET_SCORE_FC_ADV, gn_eps: float = 1e-5):
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = int(device)
+        self.n_joints, self.hidden, self.embed, self.n_blocks = n_joints, hidden, embed, n_blocks
+        desc = nat.NetDesc(kind, n_joints, hidden, embed, n_blocks, gn_eps)
+        clean = {k: v for k, v in state.items() if not k.endswith("sigmas")}
+        self._h = nat.plan_create(desc, clean, max_batch, self.device)
+        self.capacity = int(nat.lib.zedo_plan_capacity(self._h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            nat.lib.zedo_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- ScoreModelFC_Adv.forward (model.py:215-298) --------------------------------------------
+    def forward(self, x: torch.Tensor, t999: float, mode="split3") -> torch.Tensor:
+        x = _f32(x, "x")
+        B = x.shape[0]
+        out = torch.empty_like(x)
+        nat.check(nat.lib.zedo_score_forward(self._h, _ptr(x), float(t999), _ptr(out), B, _mode(mode), _stream()),
+                  "zedo_score_forward")
+        return out
+
+    # -- pc_sampler / Predictor.update_fn (sampling.py:180-205,450-527) ----------------------------
+    def sde_step(self, x: torch.Tensor, t: float, z: Optional[torch.Tensor] = None, predictor: str = "euler_maruyama",
+                 probability_flow: bool = True, beta_min: float = 0.1, beta_max: float = 20.0, n_scales: int = 1000,
+                 mode="split3") -> Tuple[torch.Tensor, torch.Tensor]:
+        x = _f32(x, "x")
+        if z is not None:
+            z = _f32(z, "z")
+        x_next, x_mean = torch.empty_like(x), torch.empty_like(x)
+        pred = {"euler_maruyama": nat.PRED_EULER_MARUYAMA, "reverse_diffusion": nat.PRED_REVERSE_DIFFUSION}[predictor]
+        nat.check(nat.lib.zedo_sde_step(self._h, _ptr(x), float(t), _ptr(z), pred, int(bool(probability_flow)),
+                                        float(beta_min), float(beta_max), int(n_scales), _ptr(x_next), _ptr(x_mean),
+                                        x.shape[0], _mode(mode), _stream()), "zedo_sde_step")
+        return x_next, x_mean
+
+    # -- the OIL loop (run/opt_main.py:202-220) ------------------------------------------------------
+    def oil_loop(self, x: torch.Tensor, T: torch.Tensor, uv: torch.Tensor, K: torch.Tensor,
+                 conf: Optional[torch.Tensor], t_sched: Sequence[float], phase_switch: Optional[int] = None,
+                 dump_steps: Iterable[int] = (), beta_min: float = 0.1, beta_max: float = 20.0, n_scales: int = 1000,
+                 mode="split3") -> Optional[torch.Tensor]:
+        """In place on ``x`` [B,J,3] and ``T`` [B,3] (and clamps ``conf`` in place like the
+        reference).  Returns the dump tensor [n_dump,B,J,3] or None."""
+        for name, t in (("x", x), ("T", T), ("uv", uv), ("K", K)):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise ValueError(f"{name} must be a contiguous float32 CUDA tensor (updated in place)")
+        if conf is not None and not (conf.is_cuda and conf.dtype == torch.float32 and conf.is_contiguous()):
+            raise ValueError("conf must be a contiguous float32 CUDA tensor")
+        ts = np.ascontiguousarray(np.asarray(t_sched, dtype=np.float32))
+        steps = int(ts.shape[0])
+        if phase_switch is None:
+            phase_switch = steps // 5
+        dump_steps = sorted(int(s) for s in dump_steps)
+        dump = None
+        if dump_steps:
+            dump = torch.empty((len(dump_steps),) + tuple(x.shape), dtype=torch.float32, device=x.device)
+        nat.check(nat.lib.zedo_oil_loop(self._h, _ptr(x), _ptr(T), _ptr(uv), _ptr(K), _ptr(conf),
+                                        ts.ctypes.data_as(C.POINTER(C.c_float)), steps, int(phase_switch),
+                                        float(beta_min), float(beta_max), int(n_scales), _ptr(dump),
+                                        nat.i32_array(dump_steps) if dump_steps else None, len(dump_steps),
+                                        x.shape[0], _mode(mode), _stream()), "zedo_oil_loop")
+        return dump
+
+
+# -- gradient_field_gen (simple_zeroshot_opt.py:46-125) ------------------------------------------------
+def grad_field(uv: torch.Tensor, x: torch.Tensor, K: torch.Tensor, conf: Optional[torch.Tensor] = None,
+               T: Optional[torch.Tensor] = None, clamp_conf_inplace: bool = True
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Returns (gradient [B,J,3], T [B,1,3]); T is solved when ``T`` is None."""
+    uv, x, K = _f32(uv, "uv"), _f32(x, "x"), _f32(K, "K")
+    B, J = x.shape[0], x.shape[1]
+    solve = T is None
+    T_buf = torch.empty((B, 3), dtype=torch.float32, device=x.device) if solve else _f32(T, "T").reshape(B, 3).clone()
+    g = torch.empty_like(x)
+    if conf is not None and not (conf.is_cuda and conf.dtype == torch.float32 and conf.is_contiguous()):
+        raise ValueError("conf must be a contiguous float32 CUDA tensor (it is clamped in place)")
+    nat.check(nat.lib.zedo_grad_field(_ptr(uv), _ptr(x), _ptr(K), _ptr(conf), _ptr(T_buf), int(solve),
+                                      int(clamp_conf_inplace), _ptr(g), None, B, J, _stream()), "zedo_grad_field")
+    return g, T_buf.reshape(B, 1, 3)
+
+
+AXES_BITS = {"x": 1, "y": 2, "z": 4}
+
+
+def axes_mask(rot_axes: str) -> int:
+    m = 0
+    for a in rot_axes:
+        m |= AXES_BITS[a]
+    return m
+
+
+# -- IPO (run/opt_main.py:175-201) ------------------------------------------------------------------------
+def ipo_fit(x0: torch.Tensor, uv: torch.Tensor, K: torch.Tensor, keylist: Sequence[int], rot_axes: str, ipo_T: float,
+            minT: float, maxT: float, iters: int = 500, b_global: Optional[int] = None, lr: float = 0.1):
+    """Returns (R [B,3,3], T [B,3], x_rot [B,J,3], qs [B,5])."""
+    x0, uv, K = _f32(x0, "x0"), _f32(uv, "uv"), _f32(K, "K")
+    B, J = x0.shape[0], x0.shape[1]
+    dev = x0.device
+    R = torch.empty((B, 3, 3), dtype=torch.float32, device=dev)
+    T = torch.empty((B, 3), dtype=torch.float32, device=dev)
+    x_rot = torch.empty_like(x0)
+    qs = torch.empty((B, 5), dtype=torch.float32, device=dev)
+    kl = nat.i32_array(keylist)
+    nat.check(nat.lib.zedo_ipo_fit(_ptr(x0), _ptr(uv), _ptr(K), kl, len(kl), axes_mask(rot_axes), float(ipo_T),
+                                   float(minT), float(maxT), int(iters), int(b_global if b_global else B), float(lr),
+                                   _ptr(R), _ptr(T), _ptr(x_rot), _ptr(qs), B, J, _stream()), "zedo_ipo_fit")
+    return R, T, x_rot, qs
+
+
+def rotopt_forward(q, scale, xk, T0, K, minT, maxT):
+    q, scale, xk, T0, K = (_f32(t, n) for t, n in ((q, "q"), (scale, "scale"), (xk, "xk"), (T0, "T0"), (K, "K")))
+    B, nk = xk.shape[0], xk.shape[1]
+    out = torch.empty((B, nk, 2), dtype=torch.float32, device=xk.device)
+    nat.check(nat.lib.zedo_rotopt_forward(_ptr(q), _ptr(scale), _ptr(xk), _ptr(T0), _ptr(K), float(minT), float(maxT),
+                                          _ptr(out), B, nk, _stream()), "zedo_rotopt_forward")
+    return out
+
+
+def rotopt_backward(q, scale, xk, T0, K, minT, maxT, d_uv):
+    q, scale, xk, T0, K, d_uv = (_f32(t, n) for t, n in ((q, "q"), (scale, "scale"), (xk, "xk"), (T0, "T0"),
+                                                         (K, "K"), (d_uv, "d_uv")))
+    B, nk = xk.shape[0], xk.shape[1]
+    d_q = torch.empty((B, 4), dtype=torch.float32, device=xk.device)
+    d_s = torch.empty((B,), dtype=torch.float32, device=xk.device)
+    nat.check(nat.lib.zedo_rotopt_backward(_ptr(q), _ptr(scale), _ptr(xk), _ptr(T0), _ptr(K), float(minT),
+                                           float(maxT), _ptr(d_uv), _ptr(d_q), _ptr(d_s), B, nk, _stream()),
+              "zedo_rotopt_backward")
+    return d_q, d_s
+
+
+# -- eval_multi + procrustes (h36m.py:365-442, transforms.py:42-148) ------------------------------------------
+def eval_multi(pred: torch.Tensor, gt: torch.Tensor, protocol2: bool = False,
+               joint_subset: Optional[Sequence[int]] = None, return_all: bool = False):
+    """pred [N,S,J,3] float32, gt [N,J,3] (converted to float64).  Returns
+    (err_min [N] f64, argmin [N] i32[, err_all [N,S] f64])."""
+    pred = _f32(pred, "pred")
+    if not gt.is_cuda:
+        raise ValueError("gt must be a CUDA tensor")
+    gt = gt.contiguous().double()
+    N, S, J = pred.shape[0], pred.shape[1], pred.shape[2]
+    err_min = torch.empty((N,), dtype=torch.float64, device=pred.device)
+    arg = torch.empty((N,), dtype=torch.int32, device=pred.device)
+    err_all = torch.empty((N, S), dtype=torch.float64, device=pred.device) if return_all else None
+    sub = nat.i32_array(joint_subset) if joint_subset is not None else None
+    nat.check(nat.lib.zedo_eval_multi(_ptr(pred), _ptr(gt), int(bool(protocol2)), N, S, J, sub,
+                                      len(sub) if sub is not None else 0, _ptr(err_min), _ptr(arg), _ptr(err_all),
+                                      _stream()), "zedo_eval_multi")
+    return (err_min, arg, err_all) if return_all else (err_min, arg)
+
+
+def aggregate_errors(err_min, actions=None) -> float:
+    """H36M: mean over actions 2..16 of the per-action means (h36m.py:424-433); otherwise the
+    plain mean (pw3d.py:338).  Host-side numpy over the [N] float64 result vector."""
+    e = err_min.detach().cpu().numpy() if hasattr(err_min, "detach") else np.asarray(err_min)
+    if actions is None:
+        return float(np.mean(e))
+    a = actions.detach().cpu().numpy() if hasattr(actions, "detach") else np.asarray(actions)
+    return float(np.mean([np.mean(e[a == k]) for k in range(2, 17)]))
+
+
+# -- sharding (rule of lib/dataset/EvaSampler.py:79-112: contiguous chunks, first N % W ranks get +1) ------
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+# -- the whole per-hypothesis pipeline (run/opt_main.py:166-222) ------------------------------------------
+def run_pose_optimisation(plan: ScorePlan, db_2d: torch.Tensor, K: torch.Tensor, clusters: torch.Tensor, cfg: dict,
+                          hypo: int = 1, mode="split3", t_start: float = 0.1, b_global: Optional[int] = None,
+                          steps: Optional[int] = None) -> torch.Tensor:
+    """db_2d [B,J,3] = (u,v,conf), K [B,3,3], clusters [S,J,3] (cluster file content).
+    Returns batch_results [B, hypo, J, 3] (the array run/opt_main.py:224 hands to eval_multi).
+    ``b_global``: batch size of the IPO loss mean when the poses are a shard of a larger batch.
+    """
+    db_2d, K, clusters = _f32(db_2d, "db_2d"), _f32(K, "K"), _f32(clusters, "clusters")
+    B, J = db_2d.shape[0], db_2d.shape[1]
+    uv = db_2d[:, :, :2].contiguous()
+    n_steps = int(cfg["OIL_iterations"] if steps is None else steps)
+    ts = linspace_schedule(t_start, float(cfg["sampling_eps"]), n_steps)
+    rel = (clusters - clusters[:, 0:1, :]).contiguous()
+    out = torch.empty((B, hypo, J, 3), dtype=torch.float32, device=db_2d.device)
+    for sid in range(hypo):
+        conf = db_2d[:, :, 2].contiguous()  # re-read per hypothesis like opt_main.py:171
+        x0 = rel[sid:sid + 1].expand(B, J, 3).contiguous()
+        _, T, x, _ = ipo_fit(x0, uv, K, cfg["IPO_keylist"], cfg["RotAxes"], cfg["IPO_T"], cfg["IPO_minScaleT"],
+                             cfg["IPO_maxScaleT"], cfg["IPO_iterations"], b_global=b_global)
+        plan.oil_loop(x, T, uv, K, conf, ts, phase_switch=n_steps // 5, mode=mode)
+        out[:, sid] = x
+    return out
