@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""Benchmark of the ZeDO per-pose optimisation loop on B200 (BASELINE.json metric: poses/s of the
+full loop = per pose S x (500 IPO iterations + 1000 OIL steps), device-timed).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]           # this implementation
+    python bench.py --impl reference [--steps K] [--warmup W]      # the CPU port of the reference path
+    torchrun --nproc-per-node N ... bench.py --gpus N ...          # one rank per GPU
+
+A "step" is one pass of the hot path over one batch of synthetic H36M-format input: BASELINE
+config 1 of `configs` index 1 -- J=17, hypo=1, 262,144 poses per GPU -- with random-init weights.
+Poses are independent, so N GPUs run N shards with no data-path collective ("weak" scaling: the
+per-GPU batch is fixed); the only exchange is one gather of the results, inside the e2e timing.
+
+One JSON line is printed by rank 0 (keys: see the task contract): `value` = poses/s with inputs
+resident in HBM, CUDA-event timed, max over ranks; `e2e` = the same loop through the public API
+with pinned-host inputs/outputs copied inside the timed region; `roofline` = the dominant kernel
+(hidden 1024x1024 layer, tcgen05 3-product split) timed live with CUDA events on the launching
+stream inside the timed region; `cpu_baseline` = the numpy oracle port on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "poses/sec (full diffusion+opt loop: 500 IPO iterations + 1000 OIL steps per pose, device-timed)"
+FLOP_PER_POSE_HIDDEN_LAYER = 2 * 1024 * 1024          # one 1024x1024 layer, per pose
+FLOP_PER_POSE_STEP = 2 * (51 * 1024 + 4 * 1024 * 1024 + 1024 * 51)  # 8,597,504
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(tflops=float(d["bf16_tflops_sustained"]), hbm=float(d["hbm_gbs"]), src="measured (sustained)")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the numpy oracle port of the reference path (oracle/ is only ever used here as the baseline)
+# ---------------------------------------------------------------------------------------------------
+def cpu_port_poses_per_s(n_poses=1024, oil_steps_sampled=100, ipo_iters=500, oil_steps_total=1000):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import zedo_oracle as zo
+    W = zo.make_weights(seed=0)
+    ds = zo.make_synthetic_dataset(n_poses, seed=1234, n_clusters=1)
+    cfg = zo.H36M_ZEDO_CFG
+    uv, K = ds["db_2d"][:, :, :2], ds["camera_param"]
+    x0 = zo.init_hypothesis(ds["clusters"], 0, n_poses)
+    t0 = time.perf_counter()
+    R, T = zo.ipo_fit(x0, uv, K, cfg["IPO_keylist"], cfg["RotAxes"], cfg["IPO_T"], cfg["IPO_minScaleT"],
+                      cfg["IPO_maxScaleT"], iters=ipo_iters)
+    t_ipo = time.perf_counter() - t0
+    x = np.einsum("bij,bnj->bni", R, x0).astype(np.float32)
+    ts = zo.oil_time_grid(oil_steps_total)[:oil_steps_sampled]
+    t0 = time.perf_counter()
+    zo.oil_loop_schedule(W, x, T, uv, K, ds["db_2d"][:, :, 2].copy(), ts, oil_steps_total // 5)
+    t_oil = time.perf_counter() - t0
+    total = t_ipo + t_oil * (oil_steps_total / oil_steps_sampled)
+    sample = (f"{n_poses} poses (BASELINE config 0 shape): {ipo_iters} IPO iterations + {oil_steps_sampled} of "
+              f"{oil_steps_total} OIL steps, OIL time scaled x{oil_steps_total / oil_steps_sampled:g}")
+    return n_poses / total, sample, dict(t_ipo_s=t_ipo, t_oil_sampled_s=t_oil)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    for _ in range(max(0, args.warmup - 2)):  # numpy/BLAS warm-up; each full sample costs ~10 s
+        cpu_port_poses_per_s(256, 5, 20)
+    vals, sample = [], ""
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps)):
+        v, sample, _ = cpu_port_poses_per_s(1024, 50)
+        vals.append(v)
+    wall = time.perf_counter() - t0
+    v = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "poses/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "H36M J=17 hypo=1, random-init concat score net (BASELINE configs[1] shape), "
+                               "CPU port of the reference path on a bounded sample", "poses_per_gpu": args.poses,
+                   "oil_steps": 1000, "ipo_iterations": 500},
+        "cpu_baseline": {"value": v, "unit": "poses/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        entry.build()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+    import zedo_release_b200 as zr
+    from zedo_release_b200 import synthetic as sy
+
+    B, S, J = args.poses, args.hypo, 17
+    cfg = dict(sy.H36M_ZEDO_CFG)
+    cfg["OIL_iterations"] = args.oil_steps
+    ds = sy.make_synthetic_dataset(B, seed=1234 + rank, n_clusters=S)
+    plan = zr.ScorePlan(sy.make_weights(seed=0), n_joints=J, max_batch=B, device=local)
+    h_db2d = torch.from_numpy(ds["db_2d"]).pin_memory()
+    h_K = torch.from_numpy(ds["camera_param"]).pin_memory()
+    h_cl = torch.from_numpy(ds["clusters"]).pin_memory()
+    h_out = torch.empty((B, S, J, 3), dtype=torch.float32).pin_memory()
+    d_db2d, d_K, d_cl = h_db2d.to(dev), h_K.to(dev), h_cl.to(dev)
+    b_global = B * world  # the IPO loss is a mean over the whole (global) batch (run/opt_main.py:191)
+
+    def step_resident():
+        return zr.run_pose_optimisation(plan, d_db2d, d_K, d_cl, cfg, hypo=S, mode=args.mode, b_global=b_global)
+
+    def step_e2e():
+        a = h_db2d.to(dev, non_blocking=True)
+        k = h_K.to(dev, non_blocking=True)
+        c = h_cl.to(dev, non_blocking=True)
+        res = zr.run_pose_optimisation(plan, a, k, c, cfg, hypo=S, mode=args.mode, b_global=b_global)
+        h_out.copy_(res, non_blocking=True)
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = zr._native.launch_count()
+    plan.profile(True, stride=53)
+    ms_total = timed(step_resident, args.steps)
+    prof = plan.profile_read()
+    plan.profile(False)
+    launches = zr._native.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps)
+    if world > 1:  # the one exchange of the path: gather of the results (here: per-shard checksum)
+        chk = torch.tensor([float(h_out.double().abs().mean())], device=dev, dtype=torch.float64)
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+    finite = bool(torch.isfinite(h_out).all())
+
+    poses_total = B * world * args.steps
+    value = poses_total / (ms_total / 1e3)
+    e2e = poses_total / (ms_e2e / 1e3)
+    peaks = load_peaks()
+    hid_ms, hid_n = prof["hidden_layer"]
+    achieved_tflops = (FLOP_PER_POSE_HIDDEN_LAYER * B) / (hid_ms / 1e3) / 1e12 if hid_ms > 0 else None
+    ncu_traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(tp):
+        try:
+            with open(tp) as f:
+                ncu_traffic = json.load(f).get("hidden_layer_dram_bytes_per_launch")
+        except Exception:
+            ncu_traffic = None
+    h2d = h_db2d.numel() * 4 + h_K.numel() * 4 + h_cl.numel() * 4
+    d2h = h_out.numel() * 4
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            v, sample, _ = cpu_port_poses_per_s(1024, 50)
+            cpu = {"value": v, "unit": "poses/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
+        line = {
+            "metric": METRIC, "value": value, "unit": "poses/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp16 hi/lo 3-product split on tcgen05, f32 accumulate)"
+            if args.mode == "split3" else args.mode, "data": "synthetic",
+            "config": {"workload": f"H36M J=17 hypo={S}, {B} synthetic poses per GPU, random-init concat score net "
+                                   f"(BASELINE configs[1]); {args.oil_steps} OIL steps + 500 IPO iterations per pose",
+                       "poses_per_gpu": B, "hypotheses": S, "oil_steps": args.oil_steps, "ipo_iterations": 500,
+                       "gemm_mode": args.mode, "parallelism": f"pose-sharded x{world}, no data-path collective",
+                       "l2": "inputs larger than L2 (2.1 GB of activations per layer pass)"},
+            "e2e": {"value": e2e, "unit": "poses/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "layer_tc_kernel<256,3,GN_SILU> (1024x1024 hidden layer)",
+                         "achieved": achieved_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                         "frac": (achieved_tflops / peaks["tflops"]) if achieved_tflops else None,
+                         "traffic": ncu_traffic, "peak_source": peaks["src"],
+                         "algorithmic_flop_per_launch": FLOP_PER_POSE_HIDDEN_LAYER * B,
+                         "mma_issue_factor": 3 if args.mode == "split3" else 1,
+                         "avg_launch_ms": hid_ms, "launches_timed": hid_n,
+                         "other_kernels_ms": {k: v[0] for k, v in prof.items() if k != "hidden_layer"}},
+            "oil_pose_steps_per_s": B * world * args.oil_steps * S / (ms_total / args.steps / 1e3),
+            "loop_tflops_algorithmic": FLOP_PER_POSE_STEP * B * world * args.oil_steps * S / (ms_total / args.steps / 1e3) / 1e12,
+            "results_finite": finite,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    plan.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--poses", type=int, default=262144, help="poses per GPU (BASELINE configs[1])")
+    ap.add_argument("--hypo", type=int, default=1)
+    ap.add_argument("--oil-steps", type=int, default=1000, help="OIL steps per pose (reference: 1000)")
+    ap.add_argument("--mode", default="split3", choices=["split3", "fp16", "fp32"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -152,6 +152,13 @@ const char* zedo_strerror(int code);
 int zedo_abi_version(void);
 /* number of kernels this library has launched in the calling process (bench.py gpu_launches) */
 int64_t zedo_launch_count(void);
+/* Live kernel timing for bench.py's roofline: while enabled, every `stride`-th launch of each
+ * kernel kind inside zedo_oil_loop / zedo_score_forward is bracketed by CUDA events on the
+ * launching stream (at most 256 samples per kind).  kinds: 0 = first layer (K=64), 1 = hidden
+ * layer (K=1024, the dominant kernel), 2 = post_dense, 3 = geometry, 4 = SDE update.
+ * zedo_plan_profile_read synchronises the recorded events and returns the mean duration. */
+int zedo_plan_profile(zedo_plan* plan, int32_t enable, int32_t stride);
+int zedo_plan_profile_read(zedo_plan* plan, int32_t kind, float* mean_ms, int32_t* n_samples);
 /* host-side helpers exposed for the CPU test-suite (no GPU needed):
  * sub-VP scalars in the reference's float32 op order (sde_lib.py:187-198). */
 int zedo_subvp_scalars(float t, float beta_min, float beta_max, float* beta_t, float* diffusion,

@@ -298,12 +298,15 @@ def test_eval_multi_golden(zr, golden):
     pred, gt = dev(g["preds"]), dev(g["gts"], torch.float64)
     for p2 in (0, 1):
         e, idx, e_all = zr.eval_multi(pred, gt, protocol2=bool(p2), return_all=True)
-        assert np.abs(e.cpu().numpy() - g[f"min_p{p2}"]).max() < 1e-9
+        # protocol 1 is exact float64; in protocol 2 the reference centres/normalises the float32
+        # prediction in float32 (numpy keeps the dtype of `pose`), the kernel in float64: ~1e-8 noise
+        tol = 2e-7 if p2 else 1e-12
+        assert np.abs(e.cpu().numpy() - g[f"min_p{p2}"]).max() < tol
         assert np.array_equal(idx.cpu().numpy(), g[f"idx_p{p2}"])  # bit-exact selection
         agg = zr.aggregate_errors(e, g["actions"])
-        assert abs(agg - float(g[f"agg_p{p2}"])) < 1e-9
-        assert np.abs(e_all.cpu().numpy().min(axis=1) - g[f"min_p{p2}"]).max() < 1e-9
-    assert abs(zr.aggregate_errors(zr.eval_multi(pred, gt, protocol2=True)[0]) - float(g["agg_pw3d_p1"])) < 1e-9
+        assert abs(agg - float(g[f"agg_p{p2}"])) < tol
+        assert np.abs(e_all.cpu().numpy().min(axis=1) - g[f"min_p{p2}"]).max() < tol
+    assert abs(zr.aggregate_errors(zr.eval_multi(pred, gt, protocol2=True)[0]) - float(g["agg_pw3d_p1"])) < 2e-7
 
 
 def test_eval_multi_large_random_and_subset(zr):
@@ -316,12 +319,13 @@ def test_eval_multi_large_random_and_subset(zr):
     sub = [1, 2, 3, 4, 5, 6, 8, 10, 11, 12, 13, 14]
     for p2 in (False, True):
         _, res, idx = zo.eval_multi(preds, gts, protocol2=p2)
+        tol = 2e-7 if p2 else 1e-12
         e, i = zr.eval_multi(dev(preds), dev(gts, torch.float64), protocol2=p2)
-        assert np.abs(e.cpu().numpy() - res).max() < 1e-9
+        assert np.abs(e.cpu().numpy() - res).max() < tol
         assert np.array_equal(i.cpu().numpy(), idx)
         _, res_s, idx_s = zo.eval_multi(preds, gts, protocol2=p2, joint_subset=sub)
         e, i = zr.eval_multi(dev(preds), dev(gts, torch.float64), protocol2=p2, joint_subset=sub)
-        assert np.abs(e.cpu().numpy() - res_s).max() < 1e-9
+        assert np.abs(e.cpu().numpy() - res_s).max() < tol
         assert np.array_equal(i.cpu().numpy(), idx_s)
 
 

@@ -22,7 +22,7 @@ EXPORTS = (
     "zedo_plan_create", "zedo_plan_destroy", "zedo_plan_capacity", "zedo_score_forward", "zedo_grad_field",
     "zedo_sde_step", "zedo_oil_loop", "zedo_ipo_fit", "zedo_rotopt_forward", "zedo_rotopt_backward",
     "zedo_eval_multi", "zedo_strerror", "zedo_abi_version", "zedo_launch_count", "zedo_subvp_scalars",
-    "zedo_blocked_offset",
+    "zedo_blocked_offset", "zedo_plan_profile", "zedo_plan_profile_read",
 )
 
 
@@ -65,6 +65,8 @@ def _load() -> C.CDLL:
         "zedo_launch_count": (i64, []),
         "zedo_subvp_scalars": (C.c_int, [f32, f32, f32, C.POINTER(f32), C.POINTER(f32), C.POINTER(f32)]),
         "zedo_blocked_offset": (i64, [i64, i64, i64, i32, i32]),
+        "zedo_plan_profile": (C.c_int, [vp, i32, i32]),
+        "zedo_plan_profile_read": (C.c_int, [vp, i32, C.POINTER(f32), C.POINTER(i32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

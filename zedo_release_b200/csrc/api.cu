@@ -116,7 +116,39 @@ struct zedo_plan {
   float* temb = nullptr;
   float* table = nullptr;  // [steps, L, H]
   std::vector<void*> owned;
+  // live kernel timing (zedo_plan_profile)
+  bool prof_on = false;
+  int prof_stride = 1;
+  int prof_seen[5] = {0, 0, 0, 0, 0};
+  struct ProfSample {
+    cudaEvent_t a, b;
+  };
+  std::vector<ProfSample> prof[5];
 };
+
+namespace {
+// brackets one launch with events when profiling is on and this launch is sampled
+struct ProfScope {
+  zedo_plan* p;
+  cudaStream_t st;
+  int kind;
+  bool active = false;
+  cudaEvent_t a{}, b{};
+  ProfScope(zedo_plan* plan, int k, cudaStream_t s) : p(plan), st(s), kind(k) {
+    if (!p->prof_on) return;
+    const int seen = p->prof_seen[kind]++;
+    if (seen % p->prof_stride != 0 || p->prof[kind].size() >= 256) return;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+    active = true;
+    cudaEventRecord(a, st);
+  }
+  ~ProfScope() {
+    if (!active) return;
+    cudaEventRecord(b, st);
+    p->prof[kind].push_back({a, b});
+  }
+};
+}  // namespace
 
 namespace {
 
@@ -226,7 +258,11 @@ int net_forward(zedo_plan* p, const float* x, const float* tbl, int64_t B, int m
     a.num_kb = w.k_pad / kBlockK;
     a.descale = w.descale;
     a.gn_eps = p->desc.gn_eps;
-    if ((rc = launch_layer_tc(a, w.bn, nprod, op.epi, p->num_sms, st))) return rc;
+    {
+      ProfScope ps(p, op.epi == EPI_LINEAR_F32 ? 2 : (a.num_kb == 1 ? 0 : 1), st);
+      rc = launch_layer_tc(a, w.bn, nprod, op.epi, p->num_sms, st);
+    }
+    if (rc) return rc;
   }
   return 0;
 }
@@ -415,10 +451,42 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
   return 0;
 }
 
+int zedo_plan_profile(zedo_plan* plan, int32_t enable, int32_t stride) {
+  if (!plan) return ZEDO_E_INVALID;
+  for (int k = 0; k < 5; ++k) {
+    for (auto& s : plan->prof[k]) {
+      cudaEventDestroy(s.a);
+      cudaEventDestroy(s.b);
+    }
+    plan->prof[k].clear();
+    plan->prof_seen[k] = 0;
+  }
+  plan->prof_on = enable != 0;
+  plan->prof_stride = stride < 1 ? 1 : stride;
+  return 0;
+}
+
+int zedo_plan_profile_read(zedo_plan* plan, int32_t kind, float* mean_ms, int32_t* n_samples) {
+  if (!plan || kind < 0 || kind >= 5 || !mean_ms || !n_samples) return ZEDO_E_INVALID;
+  double sum = 0.0;
+  int n = 0;
+  for (auto& s : plan->prof[kind]) {
+    ZEDO_CUDA_TRY(cudaEventSynchronize(s.b));
+    float ms = 0.f;
+    ZEDO_CUDA_TRY(cudaEventElapsedTime(&ms, s.a, s.b));
+    sum += ms;
+    ++n;
+  }
+  *mean_ms = n ? (float)(sum / n) : 0.f;
+  *n_samples = n;
+  return 0;
+}
+
 int zedo_plan_destroy(zedo_plan* plan) {
   if (!plan) return 0;
   cudaSetDevice(plan->device);
   cudaDeviceSynchronize();
+  zedo_plan_profile(plan, 0, 1);
   for (void* q : plan->owned) cudaFree(q);
   delete plan;
   return 0;
@@ -428,8 +496,8 @@ int zedo_score_forward(zedo_plan* plan, const float* x, float t999, float* out, 
                        void* stream) {
   int rc = check_batch(plan, B);
   if (rc) return rc;
-  if (!x || !out) return ZEDO_E_INVALID;
   if (B == 0) return 0;
+  if (!x || !out) return ZEDO_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   if ((rc = build_tables(plan, &t999, 1, st))) return rc;
   if ((rc = net_forward(plan, x, plan->table, B, gemm_mode, false, st))) return rc;
@@ -440,8 +508,9 @@ int zedo_score_forward(zedo_plan* plan, const float* x, float t999, float* out, 
 
 int zedo_grad_field(const float* uv, const float* x, const float* K, float* conf, float* T, int32_t solve_T,
                     int32_t clamp_conf_inplace, float* g, float* x_out, int64_t B, int32_t J, void* stream) {
-  if (!uv || !x || !K || !T) return ZEDO_E_INVALID;
   if (J < 1 || J > 32 || B < 0) return ZEDO_E_SHAPE;
+  if (B == 0) return 0;  // empty batch: nothing to do (empty tensors have NULL data pointers)
+  if (!uv || !x || !K || !T) return ZEDO_E_INVALID;
   return launch_grad_field(uv, x, K, conf, T, solve_T, clamp_conf_inplace, g, x_out, nullptr, B, J,
                            (cudaStream_t)stream);
 }
@@ -482,15 +551,21 @@ int zedo_oil_loop(zedo_plan* plan, float* x, float* T, const float* uv, const fl
   for (int i = 0; i < steps; ++i) {
     // gradient_field_gen + `denoise_x += joint_gradient` (opt_main.py:203-208); conf is clamped in
     // place by the first call of the reference and stays clamped
-    if ((rc = launch_grad_field(uv, x, K, conf, T, i >= phase_switch ? 1 : 0, i == 0 ? 1 : 0, nullptr, x,
-                                tc ? plan->xa : nullptr, B, J, st)))
-      return rc;
+    {
+      ProfScope ps(plan, 3, st);
+      rc = launch_grad_field(uv, x, K, conf, T, i >= phase_switch ? 1 : 0, i == 0 ? 1 : 0, nullptr, x,
+                             tc ? plan->xa : nullptr, B, J, st);
+    }
+    if (rc) return rc;
     const float* tbl = plan->table + (size_t)i * plan->L * plan->H;
     if ((rc = net_forward(plan, x, tbl, B, gemm_mode, tc, st))) return rc;
     const SdeCoef c = subvp_coef(t_sched[i], beta_min, beta_max, n_scales);
     // pc_sampler with probability_flow=True, noise_removal=True returns x_mean (sampling.py:524-527)
-    if ((rc = launch_sde_update(x, plan->eps, 64, nullptr, c, ZEDO_PRED_EULER_MARUYAMA, 1, nullptr, x, B, D, st)))
-      return rc;
+    {
+      ProfScope ps(plan, 4, st);
+      rc = launch_sde_update(x, plan->eps, 64, nullptr, c, ZEDO_PRED_EULER_MARUYAMA, 1, nullptr, x, B, D, st);
+    }
+    if (rc) return rc;
     while (next_dump < n_dump && dump_steps[next_dump] == i) {
       ZEDO_CUDA_TRY(cudaMemcpyAsync(dump + (size_t)next_dump * B * D, x, (size_t)B * D * sizeof(float),
                                     cudaMemcpyDeviceToDevice, st));
@@ -503,6 +578,7 @@ int zedo_oil_loop(zedo_plan* plan, float* x, float* T, const float* uv, const fl
 int zedo_ipo_fit(const float* x0, const float* uv, const float* K, const int32_t* keylist, int32_t nkey,
                  int32_t axes_mask, float ipo_T, float minT, float maxT, int32_t iters, int64_t B_global, float lr,
                  float* R, float* T, float* x_rot, float* qs, int64_t B, int32_t J, void* stream) {
+  if (B == 0) return 0;
   if (!x0 || !uv || !K || !keylist || !R || !T) return ZEDO_E_INVALID;
   if (nkey < 1 || nkey > 32 || J < 1 || J > 64 || iters < 0 || iters > 4096 || B < 0 || B_global < 1)
     return ZEDO_E_SHAPE;
@@ -536,6 +612,7 @@ int zedo_rotopt_backward(const float* q, const float* scale, const float* xk, co
 int zedo_eval_multi(const float* pred, const double* gt, int32_t protocol2, int64_t N, int32_t S, int32_t J,
                     const int32_t* joint_subset, int32_t n_sub, double* err_min, int32_t* argmin, double* err_all,
                     void* stream) {
+  if (N == 0) return 0;
   if (!pred || !gt || !err_min || !argmin) return ZEDO_E_INVALID;
   if (J < 1 || J > 32 || S < 1 || N < 0) return ZEDO_E_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;

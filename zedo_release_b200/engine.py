@@ -72,6 +72,20 @@ class ScorePlan:
         except Exception:
             pass
 
+    # -- live kernel timing for bench.py (CUDA events on the launching stream) ----------------------
+    PROFILE_KINDS = {"first_layer": 0, "hidden_layer": 1, "post_dense": 2, "geometry": 3, "sde_update": 4}
+
+    def profile(self, enable: bool, stride: int = 1) -> None:
+        nat.check(nat.lib.zedo_plan_profile(self._h, int(bool(enable)), int(stride)), "zedo_plan_profile")
+
+    def profile_read(self) -> Dict[str, Tuple[float, int]]:
+        out = {}
+        for name, k in self.PROFILE_KINDS.items():
+            ms, n = C.c_float(), C.c_int32()
+            nat.check(nat.lib.zedo_plan_profile_read(self._h, k, C.byref(ms), C.byref(n)), "zedo_plan_profile_read")
+            out[name] = (float(ms.value), int(n.value))
+        return out
+
     # -- ScoreModelFC_Adv.forward (model.py:215-298) --------------------------------------------
     def forward(self, x: torch.Tensor, t999: float, mode="split3") -> torch.Tensor:
         x = _f32(x, "x")
