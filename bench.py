@@ -287,7 +287,7 @@ def main():
     ap.add_argument("--poses", type=int, default=262144, help="poses per GPU (BASELINE configs[1])")
     ap.add_argument("--hypo", type=int, default=1)
     ap.add_argument("--oil-steps", type=int, default=1000, help="OIL steps per pose (reference: 1000)")
-    ap.add_argument("--mode", default="split3", choices=["split3", "fp16", "fp32"])
+    ap.add_argument("--mode", default="split3", choices=["split3", "split2", "fp16", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -39,6 +39,7 @@ extern "C" {
 #define ZEDO_GEMM_SPLIT3 0  /* tcgen05, fp16 hi/lo 3-product split: parity mode (default) */
 #define ZEDO_GEMM_FP16   1  /* tcgen05, single-pass fp16 inputs: fast mode             */
 #define ZEDO_GEMM_FP32   2  /* CUDA-core float32 FFMA: validation kernel                */
+#define ZEDO_GEMM_SPLIT2 3  /* tcgen05, fp16 activations x (hi+lo) weights: 2 MMA passes  */
 
 /* network kinds */
 #define ZEDO_NET_SCORE_FC_ADV 0  /* ScoreModelFC_Adv          (model.py:97-298)          */
@@ -164,7 +165,7 @@ int zedo_plan_profile_read(zedo_plan* plan, int32_t kind, float* mean_ms, int32_
 int zedo_subvp_scalars(float t, float beta_min, float beta_max, float* beta_t, float* diffusion,
                        float* std);
 /* byte offset of element (row, col) of a [rows, cols] fp16 operand inside the blocked,
- * 128B-swizzled layout the tcgen05 kernels read (DESIGN.md "data layout"); tile_rows = 128
+ * core-matrix-interleaved layout the tcgen05 kernels read (DESIGN.md "data layout"); tile_rows = 128
  * for activations, 256/64 for weights; hl = 0 (hi) / 1 (lo). */
 int64_t zedo_blocked_offset(int64_t row, int64_t col, int64_t cols, int32_t tile_rows, int32_t hl);
 

@@ -45,9 +45,10 @@ def test_subvp_scalars_match_oracle(built_lib):
         assert b == float(bo) and g == float(go) and s == float(so)  # same float32 op order, bit-exact
 
 
-def test_blocked_layout_is_a_swizzled_bijection(built_lib):
-    """Every (row, col, hl) of a [256, 128] operand maps to a distinct 2-byte slot; a row's eight
-    16-byte chunks are permuted by c ^ (row & 7) inside its 128-byte line (TMA SWIZZLE_128B)."""
+def test_blocked_layout_is_an_interleaved_bijection(built_lib):
+    """Every (row, col, hl) of a [256, 128] operand maps to a distinct 2-byte slot; inside a tile
+    image the eight 16-byte column chunks are the outer index and the 128 rows the inner one (the
+    K-major SWIZZLE_NONE core-matrix layout of tcgen05: SBO = 128 B, LBO = tile_rows * 16 B)."""
     rows, cols, tile = 256, 128, 128
     seen = set()
     for r in range(rows):
@@ -55,11 +56,13 @@ def test_blocked_layout_is_a_swizzled_bijection(built_lib):
             for hl in (0, 1):
                 seen.add(built_lib.blocked_offset(r, c, cols, tile, hl))
     assert len(seen) == rows * cols * 2 and min(seen) == 0 and max(seen) == rows * cols * 2 * 2 - 2
-    for r in (0, 1, 5, 7, 8, 13, 127, 128, 200):
-        base = built_lib.blocked_offset(r, 0, cols, tile, 0) & ~127
+    for r in (0, 1, 5, 7, 8, 13, 127):
         for chunk in range(8):
-            off = built_lib.blocked_offset(r, chunk * 8, cols, tile, 0)
-            assert off - base == ((chunk ^ (r & 7)) * 16)
+            assert built_lib.blocked_offset(r, chunk * 8, cols, tile, 0) == chunk * tile * 16 + r * 16
+            assert built_lib.blocked_offset(r, chunk * 8 + 3, cols, tile, 0) == chunk * tile * 16 + r * 16 + 6
+    # 8 consecutive rows of one chunk form a contiguous 128-byte core matrix
+    assert [built_lib.blocked_offset(r, 16, cols, tile, 0) for r in range(8, 16)] == \
+        [2 * tile * 16 + r * 16 for r in range(8, 16)]
     # tile (rt, kb) images are contiguous: hi image then lo image, 16 KiB each
     assert built_lib.blocked_offset(0, 0, cols, tile, 1) - built_lib.blocked_offset(0, 0, cols, tile, 0) == 16384
     assert built_lib.blocked_offset(0, 64, cols, tile, 0) == 32768

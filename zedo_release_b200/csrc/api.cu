@@ -237,8 +237,8 @@ int net_forward(zedo_plan* p, const float* x, const float* tbl, int64_t B, int m
     }
     return 0;
   }
-  if (mode != ZEDO_GEMM_SPLIT3 && mode != ZEDO_GEMM_FP16) return ZEDO_E_INVALID;
-  const int nprod = mode == ZEDO_GEMM_SPLIT3 ? 3 : 1;
+  if (mode != ZEDO_GEMM_SPLIT3 && mode != ZEDO_GEMM_FP16 && mode != ZEDO_GEMM_SPLIT2) return ZEDO_E_INVALID;
+  const int nprod = mode == ZEDO_GEMM_SPLIT3 ? 3 : (mode == ZEDO_GEMM_SPLIT2 ? 2 : 1);
   if (!xa_ready && (rc = launch_pack_x(x, p->xa, B, p->D, st))) return rc;
   for (const GemmOp& op : p->program) {
     const PackedWeight& w = p->packed[op.weight];

@@ -25,13 +25,16 @@ void count_launch(int n = 1);
     if (_e != cudaSuccess) return (int)_e;         \
   } while (0)
 
-// ---- blocked, 128B-swizzled fp16 operand layout -------------------------------------------------
+// ---- blocked, core-matrix-interleaved fp16 operand layout ------------------------------------------
 // A [rows, cols] fp16 operand (cols padded to a multiple of 64) is stored as tiles of
 // TILE_ROWS x 64 halves; tile (rt, kb) has a "hi" image followed by a "lo" image, each
-// TILE_ROWS*128 bytes.  Inside an image row r occupies bytes [r*128, r*128+128) and its eight
-// 16-byte chunks are permuted c -> c ^ (r & 7): exactly the shared-memory image a TMA
-// SWIZZLE_128B box {64, TILE_ROWS} would produce, so one linear bulk copy (cp.async.bulk)
-// of the tile is directly consumable by tcgen05.mma with a K-major SWIZZLE_128B descriptor.
+// TILE_ROWS*128 bytes.  Inside an image the eight 16-byte column chunks (8 halves each) are the
+// outer index and the rows the inner one: byte offset = chunk*(TILE_ROWS*16) + r*16.  That is the
+// canonical K-major SWIZZLE_NONE ("interleaved") UMMA layout -- 8x16B core matrices, SBO = 128 B
+// between core matrices along M/N, LBO = TILE_ROWS*16 B between the two K chunks of one MMA -- so
+//   * one linear bulk copy (cp.async.bulk) of the tile image is directly consumable by tcgen05.mma;
+//   * an epilogue warp (lane = row) writes 32 consecutive rows of one chunk = 512 contiguous bytes
+//     per store instruction (4 L1 wavefronts instead of 32 for a row-major or 128B-swizzled image).
 constexpr int kBlockK = 64;        // halves per tile row (128 bytes)
 constexpr int kActTileRows = 128;  // BLOCK_M
 
@@ -40,9 +43,8 @@ __host__ __device__ inline int64_t blocked_half_offset(int64_t row, int64_t col,
   const int64_t num_kb = cols_padded / kBlockK;
   const int64_t rt = row / tile_rows, r = row % tile_rows;
   const int64_t kb = col / kBlockK, c = col % kBlockK;
-  const int64_t chunk = (c >> 3) ^ (r & 7);
   const int64_t image = (int64_t)tile_rows * kBlockK;  // halves per hi or lo image
-  return ((rt * num_kb + kb) * 2 + hl) * image + r * kBlockK + chunk * 8 + (c & 7);
+  return ((rt * num_kb + kb) * 2 + hl) * image + (c >> 3) * ((int64_t)tile_rows * 8) + r * 8 + (c & 7);
 }
 
 __host__ __device__ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }

@@ -7,7 +7,7 @@
 // Lane j of the warp owns joint j (J <= 32); the seven normal-equation sums are xor-shuffle
 // reductions, so every lane holds the same T.  The kernel is HBM-bound: per pose it moves
 // x (r/w), uv, conf, K, T = 672 bytes at J = 17 and (optionally) emits the first GEMM's
-// fp16 hi/lo operand in the blocked swizzled layout.
+// fp16 hi/lo operand in the blocked interleaved layout (common.cuh).
 #include "kernels.cuh"
 
 namespace zedo {

@@ -18,6 +18,7 @@ struct LayerArgs {
   int m_tiles, n_tiles, num_kb;
   float descale;
   float gn_eps;
+  int dbg;  // timing experiments only (env ZEDO_DBG): 1 = no bulk copies after the first fill, 2 = no MMAs
 };
 constexpr int EPI_GN_SILU = 0, EPI_LINEAR_ACT = 1, EPI_LINEAR_F32 = 2;
 int launch_layer_tc(const LayerArgs& a, int bn, int nprod, int epi, int num_sms, cudaStream_t st);

@@ -3,20 +3,23 @@
 //   out = EPILOGUE( A[M,K] . W[N,K]^T * descale + cbias[N] (+ addend) )            (model.py:264-290)
 //
 // A and W are fp16 "hi/lo" pairs (v = hi + lo carries ~22 mantissa bits) in the blocked
-// 128B-swizzled layout of common.cuh, so every pipeline stage is filled by two linear bulk
-// async copies (cp.async.bulk -> SASS UBLKCP) that complete on an mbarrier; no tensor map.
+// core-matrix-interleaved layout of common.cuh, so every pipeline stage is filled by two linear
+// bulk async copies (cp.async.bulk -> SASS UBLKCP) that complete on an mbarrier; no tensor map.
 // The product is formed by three tcgen05.mma passes into ONE float32 TMEM accumulator:
 //   D += A_hi.W_hi ; D += A_lo.W_hi ; D += A_hi.W_lo           (ZEDO_GEMM_SPLIT3, parity mode)
+// or two passes A_hi.(W_hi + W_lo) (ZEDO_GEMM_SPLIT2: exact weights, fp16-rounded activations)
 // or a single pass A_hi.W_hi (ZEDO_GEMM_FP16, fast mode).
 //
-// CTA = 128 rows (poses) x BN columns, persistent over tiles, 6 warps:
+// CTA = 128 rows (poses) x BN columns, persistent over tiles, 10 warps:
 //   warp 0   : producer  -- one lane issues the bulk copies of a stage
 //   warp 1   : MMA issuer -- one lane issues tcgen05.mma / tcgen05.commit; owns TMEM alloc
-//   warps 2-5: epilogue  -- thread = one row (TMEM lane); tcgen05.ld 32 columns at a time;
+//   warps 2-9: epilogue  -- thread = one row (TMEM lane) x half of the columns; tcgen05.ld 32 columns at a time;
 //              GroupNorm(32 contiguous channels) is therefore thread-local: bias table add,
 //              mean/var, affine, SiLU, residual, hi/lo split, blocked store -- no shuffles.
 // TMEM holds two accumulator stages (2 x BN columns) so the epilogue of tile i overlaps the
 // MMAs of tile i+1.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace zedo {
@@ -114,15 +117,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major, 1) |
-//   [32,46) SBO >> 4 = 1024 B between 8-row groups | [46,48) version = 1 | [61,64) layout = 2 (SW128)
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+// K-major, SWIZZLE_NONE ("interleaved") shared-memory matrix descriptor (cute::UMMA::SmemDescriptor
+// bit layout): [0,14) start address >> 4 | [16,30) LBO >> 4 = byte stride between the two 16-byte K
+// chunks of one MMA (= tile_rows * 16) | [32,46) SBO >> 4 = 128 B between 8-row core matrices |
+// [46,48) version = 1 | [61,64) layout type = 0 (no swizzle).
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t tile_rows) {
   uint64_t d = (uint64_t)((smem_addr >> 4) & 0x3FFFu);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)((tile_rows * 16u) >> 4) << 16;
+  d |= (uint64_t)(128 >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
   return d;
 }
 
@@ -134,10 +137,11 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
 
 template <int BN, int NPROD>
 struct TileCfg {
+  // NPROD = 3: A_hi.W_hi + A_lo.W_hi + A_hi.W_lo | 2: A_hi.W_hi + A_hi.W_lo | 1: A_hi.W_hi
   static constexpr int kAImage = kActTileRows * kBlockK * 2;  // bytes of one hi or lo A image (16 KiB)
   static constexpr int kBImage = BN * kBlockK * 2;
   static constexpr int kABytes = kAImage * (NPROD == 3 ? 2 : 1);
-  static constexpr int kBBytes = kBImage * (NPROD == 3 ? 2 : 1);
+  static constexpr int kBBytes = kBImage * (NPROD >= 2 ? 2 : 1);
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kMaxStages = (225 * 1024) / kStageBytes;
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
@@ -145,7 +149,28 @@ struct TileCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-constexpr int kTcThreads = 192;
+constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter, each owns half the columns
+constexpr int kTcThreads = 64 + kEpiWarps * 32;    // producer warp + MMA warp + epilogue warps
+
+// hi/lo split of two floats with packed conversions (F2FP.PACK_AB instead of two F2F)
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__device__ __forceinline__ void add_hi_lo(float* v, const uint4& h4, const uint4& l4) {
+  const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+    const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+    v[2 * e] += hf.x + lf.x;
+    v[2 * e + 1] += hf.y + lf.y;
+  }
+}
 
 template <int BN, int NPROD, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1) layer_tc_kernel(const LayerArgs args) {
@@ -172,7 +197,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) layer_tc_kernel(const LayerArgs
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], kEpiWarps * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -196,10 +221,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) layer_tc_kernel(const LayerArgs
         const __half* w_src = args.W + ((int64_t)nt * num_kb) * 2 * (BN * kBlockK);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-          bulk_g2s(sA + stage * Cfg::kABytes, a_src + (int64_t)kb * 2 * (kActTileRows * kBlockK), Cfg::kABytes,
-                   &full[stage]);
-          bulk_g2s(sB + stage * Cfg::kBBytes, w_src + (int64_t)kb * 2 * (BN * kBlockK), Cfg::kBBytes, &full[stage]);
+          if ((args.dbg & 1) && (tile != (int)blockIdx.x || kb >= S)) {
+            mbar_arrive(&full[stage]);  // experiment: MMA on stale tiles, no L2->SMEM traffic
+          } else {
+            mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+            bulk_g2s(sA + stage * Cfg::kABytes, a_src + (int64_t)kb * 2 * (kActTileRows * kBlockK), Cfg::kABytes,
+                     &full[stage]);
+            bulk_g2s(sB + stage * Cfg::kBBytes, w_src + (int64_t)kb * 2 * (BN * kBlockK), Cfg::kBBytes,
+                     &full[stage]);
+          }
           if (++stage == S) {
             stage = 0;
             phase ^= 1;
@@ -225,18 +255,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) layer_tc_kernel(const LayerArgs
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * Cfg::kABytes);
           const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
-          const uint64_t a_hi = make_kmajor_sw128_desc(a_addr);
-          const uint64_t b_hi = make_kmajor_sw128_desc(b_addr);
+          const uint64_t a_hi = make_kmajor_desc(a_addr, kActTileRows);
+          const uint64_t b_hi = make_kmajor_desc(b_addr, BN);
+          // one MMA consumes K = 16 halves = two 16-byte chunks; chunks are tile_rows*16 bytes apart
+          constexpr uint32_t kAStep = (2 * kActTileRows * 16) >> 4, kBStep = (2 * BN * 16) >> 4;
+          if (args.dbg & 2) {  // experiment: feed only, no tensor work
+            umma_commit(&empty[stage]);
+            if (++stage == S) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
-            umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
+            umma_f16(d_tmem, a_hi + kAStep * k, b_hi + kBStep * k, idesc, (kb | k) != 0);
           if (NPROD == 3) {
-            const uint64_t a_lo = make_kmajor_sw128_desc(a_addr + Cfg::kAImage);
-            const uint64_t b_lo = make_kmajor_sw128_desc(b_addr + Cfg::kBImage);
+            const uint64_t a_lo = make_kmajor_desc(a_addr + Cfg::kAImage, kActTileRows);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
+            for (int k = 0; k < kBlockK / 16; ++k) umma_f16(d_tmem, a_lo + kAStep * k, b_hi + kBStep * k, idesc, 1);
+          }
+          if (NPROD >= 2) {
+            const uint64_t b_lo = make_kmajor_desc(b_addr + Cfg::kBImage, BN);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+            for (int k = 0; k < kBlockK / 16; ++k) umma_f16(d_tmem, a_hi + kAStep * k, b_lo + kBStep * k, idesc, 1);
           }
           umma_commit(&empty[stage]);  // frees the smem stage when these MMAs retire
           if (++stage == S) {
@@ -248,11 +290,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) layer_tc_kernel(const LayerArgs
       }
     }
   } else {
-    // ===================== epilogue: thread = one row =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue: thread = one row x half of the tile's columns =====================
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;   // which half of the BN columns
     const int r = q * 32 + lane;
+    constexpr int kGroupsPerWarp = BN / 64;
     const int n_total = args.n_tiles * BN;
     const int nkb_out = n_total / kBlockK;
+    constexpr int64_t kLoOff = kActTileRows * kBlockK;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int mt = tile / args.n_tiles, nt = tile - mt * args.n_tiles;
@@ -261,10 +306,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) layer_tc_kernel(const LayerArgs
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
 #pragma unroll 1
-      for (int g = 0; g < BN / 32; ++g) {
+      for (int gg = 0; gg < kGroupsPerWarp; ++gg) {
+        const int g = chalf * kGroupsPerWarp + gg;
+        const int col0 = nt * BN + g * 32;
+        // position of this thread's 32 columns inside the blocked [M_pad, N_pad] activation layout
+        const int kbo = col0 / kBlockK;
+        const int hsel = (col0 / 32) & 1;
+        // chunk c of this row lives at c * (128 rows * 8 halves) + r * 8 inside the (mt, kbo) hi image
+        const int64_t row_off =
+            (((int64_t)mt * nkb_out + kbo) * 2) * (kActTileRows * kBlockK) + (int64_t)r * 8;
+        constexpr int kChunkStride = kActTileRows * 8;
+        // residual / addend loads are issued before the TMEM read so their latency overlaps it
+        uint4 rh[4], rl[4];
+        if (EPI != EPI_LINEAR_F32 && args.resid != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int pc = (hsel * 4 + j) * kChunkStride;
+            rh[j] = *reinterpret_cast<const uint4*>(args.resid + row_off + pc);
+            rl[j] = *reinterpret_cast<const uint4*>(args.resid + row_off + kLoOff + pc);
+          }
+        }
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + g * 32), v);
-        const int col0 = nt * BN + g * 32;
         const float4* cb = reinterpret_cast<const float4*>(args.cbias + col0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -280,26 +343,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) layer_tc_kernel(const LayerArgs
           for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           continue;
         }
-        // position of this thread's 32 columns inside the blocked [M_pad, N_pad] activation layout
-        const int kbo = col0 / kBlockK;
-        const int hsel = (col0 / 32) & 1;
-        const int64_t row_off =
-            (((int64_t)mt * nkb_out + kbo) * 2) * (kActTileRows * kBlockK) + (int64_t)r * kBlockK;
-        constexpr int64_t kLoOff = kActTileRows * kBlockK;
         if (args.addend != nullptr) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int pc = ((hsel * 4 + j) ^ (r & 7)) * 8;
-            const uint4 h4 = *reinterpret_cast<const uint4*>(args.addend + row_off + pc);
-            const uint4 l4 = *reinterpret_cast<const uint4*>(args.addend + row_off + kLoOff + pc);
-            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
-              const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
-              v[8 * j + 2 * e] += hf.x + lf.x;
-              v[8 * j + 2 * e + 1] += hf.y + lf.y;
-            }
+            const int pc = (hsel * 4 + j) * kChunkStride;
+            add_hi_lo(v + 8 * j, *reinterpret_cast<const uint4*>(args.addend + row_off + pc),
+                      *reinterpret_cast<const uint4*>(args.addend + row_off + kLoOff + pc));
           }
         }
         if (EPI == EPI_GN_SILU) {
@@ -329,32 +378,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) layer_tc_kernel(const LayerArgs
         }
         if (args.resid != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int pc = ((hsel * 4 + j) ^ (r & 7)) * 8;
-            const uint4 h4 = *reinterpret_cast<const uint4*>(args.resid + row_off + pc);
-            const uint4 l4 = *reinterpret_cast<const uint4*>(args.resid + row_off + kLoOff + pc);
-            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
-              const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
-              v[8 * j + 2 * e] += hf.x + lf.x;
-              v[8 * j + 2 * e + 1] += hf.y + lf.y;
-            }
-          }
+          for (int j = 0; j < 4; ++j) add_hi_lo(v + 8 * j, rh[j], rl[j]);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __half h0, l0, h1, l1;
-            split_hi_lo(v[8 * j + 2 * e], h0, l0);
-            split_hi_lo(v[8 * j + 2 * e + 1], h1, l1);
-            hi[e] = pack_half2(h0, h1);
-            lo[e] = pack_half2(l0, l1);
-          }
-          const int pc = ((hsel * 4 + j) ^ (r & 7)) * 8;
+          for (int e = 0; e < 4; ++e) split_pair(v[8 * j + 2 * e], v[8 * j + 2 * e + 1], hi[e], lo[e]);
+          const int pc = (hsel * 4 + j) * kChunkStride;
           *reinterpret_cast<uint4*>(args.out + row_off + pc) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(args.out + row_off + kLoOff + pc) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
@@ -392,19 +423,24 @@ static int launch_one(const LayerArgs& a, int num_sms, cudaStream_t st) {
   return 0;
 }
 
-// bn: 256 (hidden layers) or 64 (post_dense); nprod: 3 (split) or 1 (fast); epi: EPI_*
-int launch_layer_tc(const LayerArgs& a, int bn, int nprod, int epi, int num_sms, cudaStream_t st) {
-  if (bn == 256 && epi == EPI_GN_SILU) {
-    return nprod == 3 ? launch_one<256, 3, EPI_GN_SILU>(a, num_sms, st) : launch_one<256, 1, EPI_GN_SILU>(a, num_sms, st);
+template <int BN, int EPI>
+static int launch_nprod(const LayerArgs& a, int nprod, int num_sms, cudaStream_t st) {
+  switch (nprod) {
+    case 3: return launch_one<BN, 3, EPI>(a, num_sms, st);
+    case 2: return launch_one<BN, 2, EPI>(a, num_sms, st);
+    case 1: return launch_one<BN, 1, EPI>(a, num_sms, st);
+    default: return ZEDO_E_INVALID;
   }
-  if (bn == 256 && epi == EPI_LINEAR_ACT) {
-    return nprod == 3 ? launch_one<256, 3, EPI_LINEAR_ACT>(a, num_sms, st)
-                      : launch_one<256, 1, EPI_LINEAR_ACT>(a, num_sms, st);
-  }
-  if (bn == 64 && epi == EPI_LINEAR_F32) {
-    return nprod == 3 ? launch_one<64, 3, EPI_LINEAR_F32>(a, num_sms, st)
-                      : launch_one<64, 1, EPI_LINEAR_F32>(a, num_sms, st);
-  }
+}
+
+// bn: 256 (hidden layers) or 64 (post_dense); nprod: 3 / 2 / 1 MMA passes; epi: EPI_*
+int launch_layer_tc(const LayerArgs& a_in, int bn, int nprod, int epi, int num_sms, cudaStream_t st) {
+  static const int dbg = getenv("ZEDO_DBG") ? atoi(getenv("ZEDO_DBG")) : 0;
+  LayerArgs a = a_in;
+  a.dbg = dbg;
+  if (bn == 256 && epi == EPI_GN_SILU) return launch_nprod<256, EPI_GN_SILU>(a, nprod, num_sms, st);
+  if (bn == 256 && epi == EPI_LINEAR_ACT) return launch_nprod<256, EPI_LINEAR_ACT>(a, nprod, num_sms, st);
+  if (bn == 64 && epi == EPI_LINEAR_F32) return launch_nprod<64, EPI_LINEAR_F32>(a, nprod, num_sms, st);
   return ZEDO_E_INVALID;
 }
 

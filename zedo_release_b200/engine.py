@@ -14,7 +14,7 @@ import torch
 
 from . import _native as nat
 
-GEMM_MODES = {"split3": nat.GEMM_SPLIT3, "fp16": nat.GEMM_FP16, "fp32": nat.GEMM_FP32}
+GEMM_MODES = {"split3": nat.GEMM_SPLIT3, "split2": nat.GEMM_SPLIT2, "fp16": nat.GEMM_FP16, "fp32": nat.GEMM_FP32}
 
 
 def _mode(mode) -> int:
