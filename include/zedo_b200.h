@@ -142,11 +142,12 @@ int zedo_rotopt_backward(const float* q, const float* scale, const float* xk, co
  * procrustes (lib/utils/transforms.py:42-148).  pred [N,S,J,3] float32, gt [N,J,3] float64
  * root-relative metres; joint_subset host int[n_sub] or NULL (all J).  Outputs per pose:
  * err_min [N] float64 = amin over hypotheses of the mean per-joint error (after Procrustes
- * when protocol2 != 0), argmin [N] int32 (first minimum wins, numpy semantics), and
- * err_all [N,S] float64 (nullable).  Computed in float64 like the reference's numpy path. */
+ * when protocol2 != 0), argmin [N] int32 (first minimum wins, numpy semantics),
+ * err_all [N,S] float64 (nullable) and aligned [N,S,J,3] float64 (nullable) = the pose that was
+ * scored (align_to_gt's output Z in protocol 2).  Computed in float64 like the reference's numpy path. */
 int zedo_eval_multi(const float* pred, const double* gt, int32_t protocol2, int64_t N, int32_t S,
                     int32_t J, const int32_t* joint_subset, int32_t n_sub, double* err_min,
-                    int32_t* argmin, double* err_all, void* stream);
+                    int32_t* argmin, double* err_all, double* aligned, void* stream);
 
 /* ---- misc ---------------------------------------------------------------------------------------- */
 const char* zedo_strerror(int code);

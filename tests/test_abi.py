@@ -32,7 +32,7 @@ def test_strerror_and_argument_errors(built_lib):
     assert "shape" in built_lib.strerror(-2)
     # NULL arguments are rejected before any CUDA call
     assert built_lib.lib.zedo_grad_field(None, None, None, None, None, 0, 0, None, None, 1, 17, None) == -1
-    assert built_lib.lib.zedo_eval_multi(None, None, 0, 1, 1, 17, None, 0, None, None, None, None) == -1
+    assert built_lib.lib.zedo_eval_multi(None, None, 0, 1, 1, 17, None, 0, None, None, None, None, None) == -1
     assert built_lib.lib.zedo_grad_field(None, None, None, None, None, 0, 0, None, None, 0, 17, None) == 0  # empty batch
     assert built_lib.lib.zedo_score_forward(None, None, 0.0, None, 1, 0, None) == -1
 

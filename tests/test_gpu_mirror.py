@@ -1,0 +1,167 @@
+"""The reference-facing mirror (zedo_release_b200.lib.*) driven the way run/opt_main.py drives the
+reference: same calls, same shapes, same return types -- checked against the golden vectors that
+oracle/gen_golden.py recorded from the real reference."""
+from types import SimpleNamespace as NS
+
+import numpy as np
+import pytest
+
+import zedo_oracle as zo
+from conftest import rel_err
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib(built_lib):
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device: there is no CPU fallback")
+    import zedo_release_b200.lib as zlib
+    zlib.install()  # `import lib...` now resolves to the mirror, as the reference drivers expect
+    return zlib
+
+
+def ref_config():
+    return NS(training=NS(sde="subvpsde", continuous=True, cond_pose_mask_prob=0.0, cond_part_mask_prob=0.0,
+                          cond_joint_mask_prob=0.0),
+              sampling=NS(method="pc", predictor="euler_maruyama", corrector="none", snr=0.16, n_steps_each=1,
+                          probability_flow=True, noise_removal=True),
+              model=NS(embedding_type="positional", scale_by_sigma=False, sigma_max=50, sigma_min=0.01,
+                       num_scales=1000, beta_min=0.1, beta_max=20.0, t=0.1, ema_rate=0.9999),
+              device=torch.device("cuda"))
+
+
+@pytest.fixture(scope="module")
+def model(lib):
+    from lib.algorithms.advanced.model import ScoreModelFC_Adv
+    m = ScoreModelFC_Adv(ref_config(), n_joints=17, joint_dim=3, hidden_dim=1024, embed_dim=512, cond_dim=3)
+    sd = {k: torch.tensor(v) for k, v in zo.make_weights(seed=0).items()}
+    sd["sigmas"] = m.sigmas.clone()
+    m.load_state_dict(sd)
+    m.to(torch.device("cuda"))
+    m.eval()
+    return m
+
+
+def test_model_forward_matches_reference(lib, model, golden):
+    g = golden("net")
+    x = torch.tensor(g["x"], device="cuda")
+    for t in (0.1, 0.05, 0.01):
+        out = model(x, torch.ones(8, device="cuda") * torch.tensor(t) * 999, torch.zeros(8, 17, 2, device="cuda"), None)
+        assert out.shape == (8, 17, 3) and rel_err(out.cpu().numpy(), g[f"out_{t}"]) < 2e-5
+    # per-row labels (never used by the drivers) still give the right rows
+    lab = torch.tensor([99.9] * 4 + [9.99] * 4, device="cuda")
+    out = model(x, lab, None, None).cpu().numpy()
+    assert rel_err(out[:4], g["out_0.1"][:4]) < 2e-5 and rel_err(out[4:], g["out_0.01"][4:]) < 2e-5
+    # a weight update invalidates the packed plan
+    with torch.no_grad():
+        model.post_dense.bias.add_(1.0)
+    out2 = model(x, torch.ones(8, device="cuda") * 99.9, None, None).cpu().numpy()
+    assert rel_err(out2, g["out_0.1"] + 1.0) < 2e-5
+    with torch.no_grad():
+        model.post_dense.bias.sub_(1.0)
+
+
+def test_driver_loop_through_the_mirror(lib, model, golden):
+    """run/opt_main.py:197-222 verbatim (100 of the 1000 steps), fed with the reference's (R, T)."""
+    from lib.algorithms.advanced import sde_lib, sampling
+    from lib.algorithms.advanced.simple_zeroshot_opt import gradient_field_gen
+    g, geo = golden("oil"), golden("geom")
+    config, device = ref_config(), torch.device("cuda")
+    sde = sde_lib.subVPSDE(beta_min=config.model.beta_min, beta_max=config.model.beta_max,
+                           N=config.model.num_scales, T=config.model.t)
+    config.sampling.probability_flow = True
+    sampling_fn = sampling.get_sampling_fn(config, sde, (16, 17, 3), lambda x: x, 0.01, device=device)
+    condition = torch.tensor(geo["db_2d"][:, :, :2], device=device).float()
+    conf = torch.tensor(geo["db_2d"][:, :, 2], device=device).float()
+    K = torch.tensor(geo["K"], device=device).float()
+    T = torch.tensor(g["T"], device=device)
+    rot_mat = torch.tensor(g["R"], device=device)
+    denoise_x = torch.tensor(g["x0"], device=device)
+    sample_num = 1000
+    timestamp = torch.linspace(sde.T, 0.01, sample_num, device=device)
+    steps = list(g["steps"])
+    with torch.no_grad():
+        denoise_x = rot_mat.bmm(denoise_x.permute(0, 2, 1)).permute(0, 2, 1).contiguous()
+        for i in range(0, 100):
+            if i < sample_num // 5:
+                joint_gradient = gradient_field_gen(condition, denoise_x, K, t=T, conf=conf, returnT=False)
+            else:
+                joint_gradient, T = gradient_field_gen(condition, denoise_x, K, conf=conf, returnT=True)
+            denoise_x += joint_gradient
+            trajs, results = sampling_fn(model, condition=condition * 0, gradient=joint_gradient,
+                                         denoise_x=denoise_x, t=timestamp[i], t_step=i, args=None)
+            assert isinstance(results, np.ndarray) and results.dtype == np.float32 and results.shape == (16, 17, 3)
+            assert trajs.shape == (1, 16, 17, 3) and np.array_equal(trajs[0], results)
+            denoise_x = torch.tensor(results).to(device)
+            if i in (0, 9, 99):
+                tol = {0: 5e-6, 9: 5e-5, 99: 5e-4}[i]
+                assert rel_err(results, g["poses"][steps.index(i)]) < tol, i
+
+
+def test_noise_bearing_predictors_through_the_mirror(lib, model, golden, monkeypatch):
+    from lib.algorithms.advanced import sde_lib, sampling
+    g, n = golden("sampler"), golden("noise")
+    z = torch.tensor(n["z"], device="cuda")
+    monkeypatch.setattr(torch, "randn_like", lambda x, *a, **k: z)  # the "identical injected noise tensors"
+    sde = sde_lib.subVPSDE(beta_min=0.1, beta_max=20.0, N=1000, T=0.1)
+    x, t = torch.tensor(g["x"], device="cuda"), torch.tensor(float(g["t"]), device="cuda")
+    for pred, kx, km in (("euler_maruyama", "em_x", "em_mean"), ("reverse_diffusion", "rd_x", "rd_mean")):
+        fn = sampling.get_pc_sampler(sde, (8, 17, 3), sampling.get_predictor(pred), sampling.get_corrector("none"),
+                                     lambda v: v, 0.16, probability_flow=False, continuous=True, denoise=False)
+        trajs, res = fn(model, condition=torch.zeros(8, 17, 2, device="cuda"), denoise_x=x, t=t, t_step=0)
+        assert rel_err(res, n[kx]) < 1e-5 and rel_err(trajs[0], n[km]) < 1e-5
+        # the generic (unfused) composition of the registered classes agrees with the fused kernel
+        score_fn = sampling.mutils.get_score_fn(sde, model, train=False, continuous=True)
+        xs, xm = sampling.get_predictor(pred)(sde, score_fn, False).update_fn(x, torch.ones(8, device="cuda") * t,
+                                                                             None, None)
+        assert rel_err(xs.cpu().numpy(), n[kx]) < 1e-5 and rel_err(xm.cpu().numpy(), n[km]) < 1e-5
+
+
+def test_rotopt_adam_loop_through_the_mirror(lib, golden):
+    """run/opt_main.py:180-195 verbatim: RotOpt + torch.optim.Adam + L1Loss, 10 iterations."""
+    from lib.algorithms.advanced.simple_zeroshot_opt import RotOpt
+    g, geo = golden("ipo"), golden("geom")
+    device = torch.device("cuda")
+    for tag, cfg in (("h36m", zo.H36M_ZEDO_CFG), ("mini", zo.MINI_ZEDO_CFG)):
+        condition = torch.tensor(geo["db_2d"][:, :, :2], device=device).float()
+        K = torch.tensor(geo["K"], device=device).float()
+        denoise_x = torch.tensor(g[f"{tag}_x0"], device=device)
+        pelvis = torch.cat((condition[:, 0, :], torch.ones((16, 1), device=device)), axis=-1)
+        T = torch.inverse(K).bmm(pelvis[:, :, None]).permute(0, 2, 1)
+        T = T / torch.norm(T, dim=-1, keepdim=True) * cfg["IPO_T"]
+        rot_opt = RotOpt(16, axis=cfg["RotAxes"], minT=cfg["IPO_minScaleT"], maxT=cfg["IPO_maxScaleT"])
+        rot_opt.to(device)
+        opt = torch.optim.Adam(rot_opt.parameters(), lr=0.1)
+        criterion = torch.nn.L1Loss(reduction='none')
+        kl = cfg["IPO_keylist"]
+        for i in range(10):
+            opt.zero_grad()
+            rot2d = rot_opt(denoise_x[:, kl, :], T, K)
+            loss = torch.mean(criterion(rot2d[:, :, :2], condition[:, kl, :2]))
+            loss.backward()
+            opt.step()
+            assert abs(float(loss) - g[f"{tag}_loss"][i]) / g[f"{tag}_loss"][i] < 1e-4
+        q = torch.cat([rot_opt.rot_vect] + [getattr(rot_opt, f"rot_vect_{a}", torch.zeros(16, 1, device=device))
+                                            for a in "xyz"], dim=-1).detach().cpu().numpy()
+        assert rel_err(q, g[f"{tag}_q_traj"][9]) < 1e-4
+        assert rel_err(rot_opt.scale.detach().cpu().numpy().reshape(16), g[f"{tag}_s_traj"][9]) < 1e-4
+        assert rot_opt.generate_matrix().shape == (16, 3, 3)
+
+
+def test_dataset_eval_multi_and_align_to_gt(lib, golden):
+    from lib.dataset.synthetic import ArrayPoseDataset
+    from lib.utils.transforms import align_to_gt
+    g = golden("eval")
+    ds = ArrayPoseDataset(g["gts"], np.zeros((30, 17, 3), np.float32), np.zeros((30, 3, 3), np.float32),
+                          actions=g["actions"])
+    for p2 in (False, True):
+        e = ds.eval_multi(g["preds"], protocol2=p2, print_verbose=False)
+        assert abs(e - float(g[f"agg_p{int(p2)}"])) < 2e-7
+        assert np.array_equal(ds.last_index, g[f"idx_p{int(p2)}"])
+    plain = ArrayPoseDataset(g["gts"], np.zeros((30, 17, 3), np.float32), np.zeros((30, 3, 3), np.float32))
+    assert abs(plain.eval_multi(g["preds"], protocol2=True) - float(g["agg_pw3d_p1"])) < 2e-7
+    for k in (0, 17, 149):  # incl. the reflected hypothesis (pose 3, hypothesis 2)
+        n, s = divmod(k, 5)
+        assert np.abs(align_to_gt(g["preds"][n, s], g["gts"][n]) - g["aligned"][k]).max() < 5e-7

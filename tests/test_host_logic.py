@@ -1,0 +1,126 @@
+"""Host-side logic that needs no GPU: sharding, schedules, synthetic generators, the mirror's
+registries and error conventions, and the world_size-2 gather over gloo."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import zedo_oracle as zo
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def zr(built_lib):
+    import zedo_release_b200 as zr
+    return zr
+
+
+def test_shard_range_matches_reference_rule(zr):
+    for n, w in ((10, 3), (65536, 8), (7, 8), (1_000_000, 8), (5, 1)):
+        spans = [zr.shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))  # contiguous, no overlap
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)  # first n % w get +1
+
+
+def test_schedule_and_synthetic_generators_match_oracle(zr, golden):
+    assert np.array_equal(zr.linspace_schedule(0.1, 0.01, 1000), golden("sde")["time_grid"])
+    assert np.array_equal(zr.linspace_schedule(0.1, 0.01, 1000), zo.oil_time_grid())
+    from zedo_release_b200 import synthetic as sy
+    a, b = zo.make_synthetic_dataset(64, seed=5, n_clusters=3), sy.make_synthetic_dataset(64, seed=5, n_clusters=3)
+    assert all(np.array_equal(a[k], b[k]) for k in a)
+    wa, wb = zo.make_weights(2, n_joints=12), sy.make_weights(2, n_joints=12)
+    assert wa.keys() == wb.keys() and all(np.array_equal(wa[k], wb[k]) for k in wa)
+    assert sy.H36M_ZEDO_CFG == zo.H36M_ZEDO_CFG and zr.axes_mask("xyz") == 7 and zr.axes_mask("z") == 4
+
+
+def test_aggregate_errors(zr):
+    e = np.arange(30, dtype=np.float64)
+    acts = 2 + np.arange(30) % 15
+    assert zr.aggregate_errors(e) == pytest.approx(e.mean())
+    assert zr.aggregate_errors(e, acts) == pytest.approx(np.mean([e[acts == a].mean() for a in range(2, 17)]))
+
+
+def test_mirror_registries_and_error_conventions(zr):
+    from zedo_release_b200.lib.algorithms.advanced import sampling, sde_lib, utils as mutils
+    from types import SimpleNamespace as NS
+    assert sampling.get_predictor("euler_maruyama") is sampling.EulerMaruyamaPredictor
+    assert sampling.get_corrector("none") is sampling.NoneCorrector
+    assert set(sampling._PREDICTORS) == {"euler_maruyama", "reverse_diffusion", "ancestral_sampling", "none"}
+    assert set(sampling._CORRECTORS) == {"langevin", "ald", "none"}
+    with pytest.raises(ValueError):  # duplicate registry name (reference sampling.py:42-43)
+        sampling.register_predictor(name="none")(type("X", (), {}))
+    sde = sde_lib.subVPSDE(beta_min=0.1, beta_max=20., N=1000, T=0.1)
+    cfg = NS(sampling=NS(method="bogus", predictor="euler_maruyama", corrector="none", snr=0.16, n_steps_each=1,
+                         probability_flow=True, noise_removal=True), training=NS(continuous=True), device="cpu")
+    with pytest.raises(ValueError):  # unknown sampler (sampling.py:125)
+        sampling.get_sampling_fn(cfg, sde, (4, 17, 3), lambda x: x, 0.01)
+    with pytest.raises(NotImplementedError):  # ancestral sampling only supports VE/VP (sampling.py:215)
+        sampling.AncestralSamplingPredictor(sde, lambda *a: None)
+    with pytest.raises(NotImplementedError):
+        mutils.get_score_fn(object(), None)
+    # sub-VP schedule of the mirror == oracle scalars
+    t = torch.tensor([0.1, 0.05, 0.01])
+    _, g = sde.sde(torch.zeros(3, 1, 1), t)
+    _, std = sde.marginal_prob(torch.zeros(3, 1, 1), t)
+    assert np.allclose(g.numpy(), zo.subvp_sde_scalars(t.numpy())[1], rtol=2e-5)
+    assert np.allclose(std.numpy(), zo.subvp_marginal_std(t.numpy()), rtol=1e-4)
+    q = torch.tensor(np.random.default_rng(0).normal(size=(5, 4)).astype(np.float32))
+    assert np.allclose(mutils.quaternion_to_matrix(q).numpy(), zo.quaternion_to_matrix(q.numpy()), atol=1e-6)
+
+
+def test_mirror_model_state_dict_contract(zr):
+    """Parameter names/shapes are the reference's (model.py:113-152) and a checkpoint with the
+    DataParallel 'module.' prefix loads the way run/opt_main.py:125-136 does it."""
+    from zedo_release_b200.lib.algorithms.advanced.model import ScoreModelFC_Adv
+    from zedo_release_b200.lib.algorithms.ema import ExponentialMovingAverage
+    from types import SimpleNamespace as NS
+    cfg = NS(model=NS(embedding_type="positional", scale_by_sigma=False, sigma_max=50, sigma_min=0.01,
+                      num_scales=1000, ema_rate=0.9999),
+             training=NS(cond_pose_mask_prob=0.0, cond_part_mask_prob=0.0, cond_joint_mask_prob=0.0))
+    m = ScoreModelFC_Adv(cfg, n_joints=17, joint_dim=3, hidden_dim=1024, embed_dim=512, cond_dim=3)
+    W = zo.make_weights(seed=0)
+    names = set(m.state_dict().keys())
+    assert names == set(W.keys()) | {"sigmas"}
+    ckpt = {"model_state_dict": {"module." + k: torch.tensor(v) for k, v in W.items()},
+            "ema": ExponentialMovingAverage(m.parameters(), 0.9999).state_dict(), "step": 7}
+    ckpt["model_state_dict"]["module.sigmas"] = m.sigmas.clone()
+    m.load_state_dict({k[7:]: v for k, v in ckpt["model_state_dict"].items()})
+    ema = ExponentialMovingAverage(m.parameters(), decay=cfg.model.ema_rate)
+    ema.load_state_dict(ckpt["ema"])
+    assert np.array_equal(m.b2_dense1.weight.detach().numpy(), W["b2_dense1.weight"])
+    assert sum(p.numel() for p in m.parameters()) == 7_203_379
+    with pytest.raises(RuntimeError):  # model on CPU: no CPU path
+        m.eval()
+        m(torch.zeros(2, 17, 3), torch.ones(2), None, None)
+
+
+def _gloo_worker(rank, world, port, n, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from zedo_release_b200 import parallel
+    r, w, _ = parallel.init_from_env("gloo")
+    lo, hi = parallel.shard_range(n, r, w)
+    full = torch.arange(n * 6, dtype=torch.float32).reshape(n, 2, 3)
+    got = parallel.gather_rows(full[lo:hi].clone(), n)
+    idx = parallel.gather_rows(torch.arange(lo, hi, dtype=torch.int32), n)
+    ok = torch.equal(got, full) and torch.equal(idx, torch.arange(n, dtype=torch.int32))
+    open(os.path.join(out_dir, f"rank{rank}.txt"), "w").write("ok" if ok else "bad")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [10, 7, 64])
+def test_gather_rows_world2_gloo(built_lib, tmp_path, n):
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_gloo_worker, args=(2, port, n, str(tmp_path)), nprocs=2, join=True)
+    assert [open(tmp_path / f"rank{r}.txt").read() for r in range(2)] == ["ok", "ok"]

@@ -59,7 +59,7 @@ def _load() -> C.CDLL:
                                    i64, i32, vp]),
         "zedo_rotopt_forward": (C.c_int, [p, p, p, p, p, f32, f32, p, i64, i32, vp]),
         "zedo_rotopt_backward": (C.c_int, [p, p, p, p, p, f32, f32, p, p, p, i64, i32, vp]),
-        "zedo_eval_multi": (C.c_int, [p, p, i32, i64, i32, i32, C.POINTER(i32), i32, p, p, p, vp]),
+        "zedo_eval_multi": (C.c_int, [p, p, i32, i64, i32, i32, C.POINTER(i32), i32, p, p, p, p, vp]),
         "zedo_strerror": (C.c_char_p, [C.c_int]),
         "zedo_abi_version": (C.c_int, []),
         "zedo_launch_count": (i64, []),

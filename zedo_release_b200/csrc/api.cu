@@ -611,7 +611,7 @@ int zedo_rotopt_backward(const float* q, const float* scale, const float* xk, co
 
 int zedo_eval_multi(const float* pred, const double* gt, int32_t protocol2, int64_t N, int32_t S, int32_t J,
                     const int32_t* joint_subset, int32_t n_sub, double* err_min, int32_t* argmin, double* err_all,
-                    void* stream) {
+                    double* aligned, void* stream) {
   if (N == 0) return 0;
   if (!pred || !gt || !err_min || !argmin) return ZEDO_E_INVALID;
   if (J < 1 || J > 32 || S < 1 || N < 0) return ZEDO_E_SHAPE;
@@ -622,7 +622,7 @@ int zedo_eval_multi(const float* pred, const double* gt, int32_t protocol2, int6
     ZEDO_CUDA_TRY(cudaMallocAsync((void**)&sub, (size_t)n_sub * sizeof(int), st));
     ZEDO_CUDA_TRY(cudaMemcpyAsync(sub, joint_subset, (size_t)n_sub * sizeof(int), cudaMemcpyHostToDevice, st));
   }
-  int rc = launch_eval_multi(pred, gt, protocol2, N, S, J, sub, n_sub, err_min, argmin, err_all, st);
+  int rc = launch_eval_multi(pred, gt, protocol2, N, S, J, sub, n_sub, err_min, argmin, err_all, aligned, st);
   if (sub) cudaFreeAsync(sub, st);
   return rc;
 }

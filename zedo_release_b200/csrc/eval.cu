@@ -52,7 +52,7 @@ __device__ void svd3x3_onesided(double* M, double* V) {
 __global__ void __launch_bounds__(128)
 eval_multi_kernel(const float* __restrict__ pred, const double* __restrict__ gt, int protocol2, int64_t N, int S,
                   int J, const int* __restrict__ subset, int n_sub, double* __restrict__ err_min,
-                  int* __restrict__ argmin, double* __restrict__ err_all) {
+                  int* __restrict__ argmin, double* __restrict__ err_all, double* __restrict__ aligned) {
   const int lane = threadIdx.x & 31;
   const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= N) return;
@@ -118,6 +118,12 @@ eval_multi_kernel(const float* __restrict__ pred, const double* __restrict__ gt,
       p1 = k * (b0 * Rm[1] + b1 * Rm[4] + b2 * Rm[7]) + am1;
       p2 = k * (b0 * Rm[2] + b1 * Rm[5] + b2 * Rm[8]) + am2;
     }
+    if (aligned != nullptr && active) {  // the pose eval_multi scores (align_to_gt output in protocol 2)
+      double* ap = aligned + ((n * S + s) * J + lane) * 3;
+      ap[0] = p0;
+      ap[1] = p1;
+      ap[2] = p2;
+    }
     const double d0 = p0 - g0, d1 = p1 - g1, d2 = p2 - g2;
     const double e = counted ? sqrt(d0 * d0 + d1 * d1 + d2 * d2) : 0.0;
     const double err = warp_sum_d(e) / n_counted;
@@ -135,11 +141,11 @@ eval_multi_kernel(const float* __restrict__ pred, const double* __restrict__ gt,
 
 int launch_eval_multi(const float* pred, const double* gt, int protocol2, int64_t N, int S, int J,
                       const int* subset_dev, int n_sub, double* err_min, int* argmin, double* err_all,
-                      cudaStream_t st) {
+                      double* aligned, cudaStream_t st) {
   if (N == 0) return 0;
   const int warps = 4;
   eval_multi_kernel<<<(unsigned)((N + warps - 1) / warps), warps * 32, 0, st>>>(pred, gt, protocol2, N, S, J, subset_dev,
-                                                                             n_sub, err_min, argmin, err_all);
+                                                                             n_sub, err_min, argmin, err_all, aligned);
   ZEDO_LAUNCH_CHECK();
   return 0;
 }

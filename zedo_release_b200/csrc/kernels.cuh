@@ -45,7 +45,7 @@ int launch_rotopt_backward(const float* q, const float* scale, const float* xk, 
                            cudaStream_t st);
 int launch_eval_multi(const float* pred, const double* gt, int protocol2, int64_t N, int S, int J,
                       const int* subset_dev, int n_sub, double* err_min, int* argmin, double* err_all,
-                      cudaStream_t st);
+                      double* aligned, cudaStream_t st);
 
 
 }  // namespace zedo

@@ -205,9 +205,9 @@ def rotopt_backward(q, scale, xk, T0, K, minT, maxT, d_uv):
 
 # -- eval_multi + procrustes (h36m.py:365-442, transforms.py:42-148) ------------------------------------------
 def eval_multi(pred: torch.Tensor, gt: torch.Tensor, protocol2: bool = False,
-               joint_subset: Optional[Sequence[int]] = None, return_all: bool = False):
+               joint_subset: Optional[Sequence[int]] = None, return_all: bool = False, return_aligned: bool = False):
     """pred [N,S,J,3] float32, gt [N,J,3] (converted to float64).  Returns
-    (err_min [N] f64, argmin [N] i32[, err_all [N,S] f64])."""
+    (err_min [N] f64, argmin [N] i32[, err_all [N,S] f64][, aligned [N,S,J,3] f64])."""
     pred = _f32(pred, "pred")
     if not gt.is_cuda:
         raise ValueError("gt must be a CUDA tensor")
@@ -216,11 +216,17 @@ def eval_multi(pred: torch.Tensor, gt: torch.Tensor, protocol2: bool = False,
     err_min = torch.empty((N,), dtype=torch.float64, device=pred.device)
     arg = torch.empty((N,), dtype=torch.int32, device=pred.device)
     err_all = torch.empty((N, S), dtype=torch.float64, device=pred.device) if return_all else None
+    aligned = torch.empty((N, S, J, 3), dtype=torch.float64, device=pred.device) if return_aligned else None
     sub = nat.i32_array(joint_subset) if joint_subset is not None else None
     nat.check(nat.lib.zedo_eval_multi(_ptr(pred), _ptr(gt), int(bool(protocol2)), N, S, J, sub,
                                       len(sub) if sub is not None else 0, _ptr(err_min), _ptr(arg), _ptr(err_all),
-                                      _stream()), "zedo_eval_multi")
-    return (err_min, arg, err_all) if return_all else (err_min, arg)
+                                      _ptr(aligned), _stream()), "zedo_eval_multi")
+    out = (err_min, arg)
+    if return_all:
+        out += (err_all,)
+    if return_aligned:
+        out += (aligned,)
+    return out
 
 
 def aggregate_errors(err_min, actions=None) -> float:

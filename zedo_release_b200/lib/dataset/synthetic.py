@@ -1,0 +1,52 @@
+"""A dataset object with the attribute contract the drivers rely on (run/opt_main.py:115-118,227-228):
+``db_3d`` [N,J,3], ``db_2d`` [N,J,3] = (u, v, conf), ``camera_param`` [N,3,3] and
+``eval_multi(preds, protocol2=..., print_verbose=...)``.  File loaders of the reference
+(lib/dataset/*.py) are I/O and out of scope; this one is filled from arrays (e.g. the synthetic
+H36M-format generator).  ``eval_multi`` follows lib/dataset/h36m.py:365-442 (action-wise mean over
+actions 2..16) when ``actions`` is given, else lib/dataset/pw3d.py:286-345 (plain mean), and runs
+on the GPU (csrc/eval.cu)."""
+import numpy as np
+import torch
+
+from zedo_release_b200 import engine
+from zedo_release_b200 import synthetic as _syn
+
+
+class ArrayPoseDataset:
+    def __init__(self, db_3d, db_2d, camera_param, actions=None, joint_subset=None, name="synthetic"):
+        self.db_3d = np.asarray(db_3d)
+        self.db_2d = np.asarray(db_2d, dtype=np.float32)
+        self.camera_param = np.asarray(camera_param, dtype=np.float32)
+        self.actions = None if actions is None else np.asarray(actions)
+        self.joint_subset = joint_subset
+        self.name = name
+        self.last_index = None  # argmin over hypotheses of the last eval_multi call
+
+    @classmethod
+    def synthetic_h36m(cls, n_poses, seed=1234, detected_2d=True):
+        ds = _syn.make_synthetic_dataset(n_poses, n_joints=17, seed=seed, detected_2d=detected_2d)
+        return cls(ds["db_3d"], ds["db_2d"], ds["camera_param"], actions=ds["actions"], name="h36m-synthetic")
+
+    def __len__(self):
+        return len(self.db_3d)
+
+    def eval_multi(self, preds, protocol2=False, print_verbose=False, sample_interval=None, valid_ind=None):
+        """preds [N, m, j, 3] -> scalar error in metres; per pose the minimum over the m hypotheses of
+        the mean per-joint error (after Procrustes alignment when protocol2)."""
+        if valid_ind is not None:
+            raise NotImplementedError("valid_ind filtering is not implemented")
+        assert len(preds) == len(self.db_3d)
+        gt = self.db_3d - self.db_3d[:, 0:1]
+        actions = self.actions
+        if sample_interval is not None:
+            preds, gt = preds[::sample_interval], gt[::sample_interval]
+            actions = None if actions is None else actions[::sample_interval]
+        dev = torch.device("cuda", torch.cuda.current_device())
+        p = torch.as_tensor(np.ascontiguousarray(preds, dtype=np.float32), device=dev)
+        g = torch.as_tensor(np.ascontiguousarray(gt, dtype=np.float64), device=dev)
+        err, idx = engine.eval_multi(p, g, protocol2=protocol2, joint_subset=self.joint_subset)
+        self.last_index = idx.cpu().numpy()
+        error = engine.aggregate_errors(err, actions)
+        if print_verbose:
+            print(f"{self.name} {'p2' if protocol2 else 'p1'}: {error:.5f}")
+        return error

@@ -1,0 +1,78 @@
+"""Multi-GPU plumbing: one process per GPU, poses sharded contiguously, no collective inside the
+loop; one gather of the results (and of the per-pose errors) at the end.
+
+Sharding rule = lib/dataset/EvaSampler.py:79-112 of the reference (contiguous chunks, the first
+``N % W`` ranks get one extra item).  The gather works with the NCCL backend (CUDA tensors, NVLink)
+and with gloo (CPU tensors; used by the world_size-2 tests).
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .engine import shard_range
+
+
+def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """(rank, world, local_rank) from the torchrun environment; initialises the process group when
+    WORLD_SIZE > 1 (MASTER_ADDR should be 127.0.0.1 on a single node)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend, **kw)
+    return rank, world, local
+
+
+def shard_sizes(n: int, world: int) -> List[int]:
+    return [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
+
+
+def gather_rows(local: torch.Tensor, n_total: int) -> torch.Tensor:
+    """All ranks contribute their contiguous row shard ``local`` [n_r, ...]; every rank receives the
+    full [n_total, ...] tensor in pose order.  Uneven shards are padded to the largest one."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        assert local.shape[0] == n_total
+        return local
+    world = dist.get_world_size()
+    sizes = shard_sizes(n_total, world)
+    assert local.shape[0] == sizes[dist.get_rank()], "local shard does not follow shard_range()"
+    width = max(sizes)
+    pad = torch.zeros((width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((world * width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad.contiguous())
+    out = out.reshape((world, width) + tuple(local.shape[1:]))
+    return torch.cat([out[r, : sizes[r]] for r in range(world)], dim=0)
+
+
+def run_sharded(plan_factory, db_2d, K, clusters, cfg, hypo=1, mode="split3", gt=None, protocol2=False,
+                actions=None):
+    """The whole job on this rank's shard: slice the (host) arrays by ``shard_range``, run IPO + OIL
+    (IPO gradients scaled by the GLOBAL batch: the reference's loss is a mean over the whole batch,
+    run/opt_main.py:191), optionally evaluate, gather.  Returns (results [N,S,J,3] on every rank,
+    (err_min [N], argmin [N]) or None)."""
+    from . import engine
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    n = db_2d.shape[0]
+    lo, hi = shard_range(n, rank, world)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    plan = plan_factory(hi - lo)
+    res = engine.run_pose_optimisation(plan, torch.as_tensor(db_2d[lo:hi], device=dev),
+                                       torch.as_tensor(K[lo:hi], device=dev), torch.as_tensor(clusters, device=dev),
+                                       cfg, hypo=hypo, mode=mode, b_global=n)
+    ev = None
+    if gt is not None:
+        err, idx = engine.eval_multi(res, torch.as_tensor(gt[lo:hi], device=dev), protocol2=protocol2)
+        ev = (gather_rows(err, n), gather_rows(idx, n))
+    return gather_rows(res, n), ev
