@@ -3,6 +3,7 @@
 // lives in its own translation unit.
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -101,7 +102,9 @@ struct zedo_plan {
   float* beta = nullptr;
   float* post_bias = nullptr;  // [64]
   std::vector<PackedWeight> packed;
+  std::vector<PackedWeight> packed_pair;  // 1024 -> 1024 layers again, 128-row tiles for the CTA-pair kernel
   std::vector<GemmOp> program;
+  bool use_pairs = true;
 
   // workspaces
   __half* xa = nullptr;            // [m_pad, 64] blocked hi/lo
@@ -260,7 +263,14 @@ int net_forward(zedo_plan* p, const float* x, const float* tbl, int64_t B, int m
     a.gn_eps = p->desc.gn_eps;
     {
       ProfScope ps(p, op.epi == EPI_LINEAR_F32 ? 2 : (a.num_kb == 1 ? 0 : 1), st);
-      rc = launch_layer_tc(a, w.bn, nprod, op.epi, p->num_sms, st);
+      const PackedWeight& wp = p->packed_pair[op.weight];
+      if (p->use_pairs && wp.dev != nullptr && op.epi != EPI_LINEAR_F32) {
+        a.W = wp.dev;                        // CTA-pair kernel: 256 poses x 256 channels per cluster
+        a.m_tiles = (m_tiles + 1) & ~1;      // activation buffers are padded to 256 rows
+        rc = launch_layer_tc2(a, nprod, op.epi, p->num_sms, st);
+      } else {
+        rc = launch_layer_tc(a, w.bn, nprod, op.epi, p->num_sms, st);
+      }
     }
     if (rc) return rc;
   }
@@ -327,7 +337,8 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
   p->E = E;
   p->L = 1 + 2 * NB;
   p->cap = max_batch;
-  p->m_pad = round_up(max_batch, kActTileRows);
+  p->m_pad = round_up(max_batch, 2 * kActTileRows);  // CTA pairs work on 256 rows
+  p->use_pairs = !(getenv("ZEDO_TC2") && atoi(getenv("ZEDO_TC2")) == 0);
   int rc = 0;
 #define PLAN_TRY(expr)         \
   do {                         \
@@ -387,6 +398,12 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
     PLAN_TRY(pack_weight(w->data(), H, K, 256, &pw));
     p->owned.push_back(pw.dev);
     p->packed.push_back(pw);
+    PackedWeight pw2;
+    if (K == H) {
+      PLAN_TRY(pack_weight(w->data(), H, K, 128, &pw2));
+      p->owned.push_back(pw2.dev);
+    }
+    p->packed_pair.push_back(pw2);
     float* w32 = nullptr;
     PLAN_TRY(upload(p, &w32, w->data(), w->size()));
     p->w32.push_back(w32);
@@ -400,6 +417,7 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
     PLAN_TRY(pack_weight(w->data(), D, H, 64, &pw));
     p->owned.push_back(pw.dev);
     p->packed.push_back(pw);
+    p->packed_pair.push_back(PackedWeight());
     float* w32 = nullptr;
     PLAN_TRY(upload(p, &w32, w->data(), w->size()));
     p->w32.push_back(w32);

@@ -22,6 +22,7 @@ struct LayerArgs {
 };
 constexpr int EPI_GN_SILU = 0, EPI_LINEAR_ACT = 1, EPI_LINEAR_F32 = 2;
 int launch_layer_tc(const LayerArgs& a, int bn, int nprod, int epi, int num_sms, cudaStream_t st);
+int launch_layer_tc2(const LayerArgs& a, int nprod, int epi, int num_sms, cudaStream_t st);
 int launch_grad_field(const float* uv, const float* x, const float* K, float* conf, float* T, int solve_T,
                       int clamp_inplace, float* g, float* x_out, __half* xa, int64_t B, int J, cudaStream_t st);
 int launch_pack_x(const float* x, __half* xa, int64_t B, int D, cudaStream_t st);

@@ -1,0 +1,261 @@
+// K1, CTA-pair version for the 1024 -> 1024 layers: tcgen05.mma.cta_group::2, M = 256 per pair.
+//
+// A cluster of two CTAs (one TPC = two SMs) computes 256 poses x 256 channels.  Each CTA stages
+// only ITS 128 rows of A (hi+lo, 32 KiB) and ITS half (128 channels) of the W tile (hi+lo, 32 KiB)
+// per 64-wide k-block: 64 KiB per stage instead of 96, so three stages fit (the one-CTA kernel is
+// limited to two and stalls on load latency) and the L2 -> SMEM traffic per flop drops by a third.
+// The leader CTA's MMA lane issues every tcgen05.mma for the pair; accumulator rows 0-127 land in the
+// leader's TMEM, rows 128-255 in the peer's, so each CTA's epilogue warps drain their own TMEM exactly
+// as in mlp_tc.cu.
+//
+// Cross-CTA signalling (non-tensor bulk copies cannot signal a peer mbarrier, so the peer relays):
+//   full[s]       own bulk copies landed (per CTA)
+//   peer_full[s]  leader only: the peer's relay lane observed its full[s] and arrived remotely
+//   empty[s]      tcgen05.commit multicast (mask 0b11): the MMAs that read stage s in BOTH CTAs retired
+//   tmem_full[a]  tcgen05.commit multicast: accumulator a complete in both TMEMs
+//   tmem_empty[a] leader only, count 16: one arrive per epilogue warp of both CTAs (peer: remote)
+#include <cstdlib>
+
+#include "tc_common.cuh"
+
+namespace zedo {
+
+__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// arrive (once all prior MMAs of this thread retire) on the barrier at this offset in both CTAs
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+
+template <int NPROD>
+struct PairCfg {
+  static constexpr int kBN = 256;                              // channels per pair tile
+  static constexpr int kHalfN = 128;                           // W rows staged by each CTA
+  static constexpr int kAImage = kActTileRows * kBlockK * 2;   // 16 KiB
+  static constexpr int kBImage = kHalfN * kBlockK * 2;         // 16 KiB
+  static constexpr int kABytes = kAImage * (NPROD == 3 ? 2 : 1);
+  static constexpr int kBBytes = kBImage * (NPROD >= 2 ? 2 : 1);
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kMaxStages = (225 * 1024) / kStageBytes;
+  static constexpr int kStages = kMaxStages > 6 ? 6 : kMaxStages;
+  static constexpr int kTmemCols = 2 * kBN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int NPROD, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) layer_tc2_kernel(const LayerArgs args) {
+  using Cfg = PairCfg<NPROD>;
+  constexpr int S = Cfg::kStages;
+  constexpr int BN = Cfg::kBN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + S * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* peer_full = bars + S;
+  uint64_t* empty = bars + 2 * S;
+  uint64_t* tmem_full = bars + 3 * S;
+  uint64_t* tmem_empty = bars + 3 * S + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&peer_full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * kEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster_sync_all();  // both CTAs' barriers exist before anyone signals across the pair
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_kb = args.num_kb;
+  const int num_pairs = (args.m_tiles / 2) * args.n_tiles;  // m_tiles is even (plan pads to 256 rows)
+  const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ===================== producer (both CTAs): own A rows + own half of W =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = pair0; pt < num_pairs; pt += pair_stride) {
+        const int mp = pt / args.n_tiles, nt = pt - mp * args.n_tiles;
+        const int mt = 2 * mp + (int)rank;
+        const __half* a_src = args.A + ((int64_t)mt * num_kb) * 2 * (kActTileRows * kBlockK);
+        const __half* w_src = args.W + ((int64_t)(2 * nt + (int)rank) * num_kb) * 2 * (Cfg::kHalfN * kBlockK);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+          bulk_g2s(sA + stage * Cfg::kABytes, a_src + (int64_t)kb * 2 * (kActTileRows * kBlockK), Cfg::kABytes,
+                   &full[stage]);
+          bulk_g2s(sB + stage * Cfg::kBBytes, w_src + (int64_t)kb * 2 * (Cfg::kHalfN * kBlockK), Cfg::kBBytes,
+                   &full[stage]);
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      if (leader) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        constexpr uint32_t idesc = make_idesc_f16(256, BN);
+        int it = 0;
+        for (int pt = pair0; pt < num_pairs; pt += pair_stride, ++it) {
+          const int as = it & 1;
+          const uint32_t aphase = (it >> 1) & 1;
+          mbar_wait(&tmem_empty[as], aphase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full[stage], phase);
+            mbar_wait(&peer_full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(sA + stage * Cfg::kABytes);
+            const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
+            const uint64_t a_hi = make_kmajor_desc(a_addr, kActTileRows);
+            const uint64_t b_hi = make_kmajor_desc(b_addr, Cfg::kHalfN);
+            constexpr uint32_t kAStep = (2 * kActTileRows * 16) >> 4, kBStep = (2 * Cfg::kHalfN * 16) >> 4;
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16_2cta(d_tmem, a_hi + kAStep * k, b_hi + kBStep * k, idesc, (kb | k) != 0);
+            if (NPROD == 3) {
+              const uint64_t a_lo = make_kmajor_desc(a_addr + Cfg::kAImage, kActTileRows);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_f16_2cta(d_tmem, a_lo + kAStep * k, b_hi + kBStep * k, idesc, 1);
+            }
+            if (NPROD >= 2) {
+              const uint64_t b_lo = make_kmajor_desc(b_addr + Cfg::kBImage, Cfg::kHalfN);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_f16_2cta(d_tmem, a_hi + kAStep * k, b_lo + kBStep * k, idesc, 1);
+            }
+            umma_commit_2cta(&empty[stage]);
+            if (++stage == S) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          umma_commit_2cta(&tmem_full[as]);
+        }
+      } else {
+        // ===================== relay (peer CTA): tell the leader this CTA's stage has landed =====================
+        for (int pt = pair0; pt < num_pairs; pt += pair_stride) {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full[stage], phase);
+            mbar_arrive_cluster(&peer_full[stage], 0);
+            if (++stage == S) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs): own 128 rows =====================
+    const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    int it = 0;
+    for (int pt = pair0; pt < num_pairs; pt += pair_stride, ++it) {
+      const int mp = pt / args.n_tiles, nt = pt - mp * args.n_tiles;
+      const int mt = 2 * mp + (int)rank;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      epilogue_tile<BN, EPI>(args, tmem_base + (uint32_t)(as * BN), q, chalf, r, mt, nt);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty[as], 0);  // the leader's MMA lane owns accumulator reuse
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();  // nobody leaves while the partner may still read its SMEM / signal its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int NPROD, int EPI>
+static int launch_pair(const LayerArgs& a, int num_sms, cudaStream_t st) {
+  using Cfg = PairCfg<NPROD>;
+  static bool configured = false;
+  auto kern = layer_tc2_kernel<NPROD, EPI>;
+  if (!configured) {
+    ZEDO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  if (a.m_tiles % 2 != 0) return ZEDO_E_SHAPE;
+  const int pairs = (a.m_tiles / 2) * a.n_tiles;
+  if (pairs == 0) return 0;
+  const int max_pairs = num_sms / 2;
+  const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
+  kern<<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(a);
+  ZEDO_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int EPI>
+static int launch_pair_nprod(const LayerArgs& a, int nprod, int num_sms, cudaStream_t st) {
+  switch (nprod) {
+    case 3: return launch_pair<3, EPI>(a, num_sms, st);
+    case 2: return launch_pair<2, EPI>(a, num_sms, st);
+    case 1: return launch_pair<1, EPI>(a, num_sms, st);
+    default: return ZEDO_E_INVALID;
+  }
+}
+
+// hidden layers (N multiple of 256, weights packed with 128-row tiles); a.m_tiles must be even
+int launch_layer_tc2(const LayerArgs& a, int nprod, int epi, int num_sms, cudaStream_t st) {
+  if (epi == EPI_GN_SILU) return launch_pair_nprod<EPI_GN_SILU>(a, nprod, num_sms, st);
+  if (epi == EPI_LINEAR_ACT) return launch_pair_nprod<EPI_LINEAR_ACT>(a, nprod, num_sms, st);
+  return ZEDO_E_INVALID;
+}
+
+}  // namespace zedo
