@@ -131,6 +131,33 @@ def test_score_forward_j12_and_block_count(zr, golden):
     assert e.value.code == -2
 
 
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("split3", 2e-5)])
+def test_control_network_forward_and_loop(zr, golden, mode, tol):
+    """Control_ScoreModelFC_Adv (the infant network, control_model.py:277-382): forward against the golden
+    vector recorded from the reference, a random batch against the oracle, and a few OIL steps with the
+    infant phase switch."""
+    from zedo_release_b200 import _native as nat
+    g = golden("control")
+    W = zo.make_weights(seed=int(g["weights_seed"]), control=True)
+    p = zr.ScorePlan(W, n_joints=17, max_batch=512, device=0, kind=nat.NET_CONTROL)
+    out = p.forward(dev(g["x"]), float(g["t999"]), mode=mode)
+    assert rel_err(out.cpu().numpy(), g["out"]) < tol
+    x = np.random.default_rng(4).normal(0, 0.4, (300, 17, 3)).astype(np.float32)
+    for t999 in (99.9, 10.3):
+        ref = zo.control_score_forward(W, x, np.float32(t999))
+        assert rel_err(p.forward(dev(x), t999, mode=mode).cpu().numpy(), ref) < tol
+    ds = zo.make_synthetic_dataset(64, seed=9)
+    uv, K, conf = ds["db_2d"][:, :, :2], ds["camera_param"], ds["db_2d"][:, :, 2]
+    x0 = (ds["db_3d"] + 0.05).astype(np.float32)
+    T0 = zo.init_translation(uv, K, 1.0)
+    ts = zo.oil_time_grid()[940:952]
+    xg, Tg = dev(x0), dev(T0.reshape(64, 3))
+    p.oil_loop(xg, Tg, dev(uv), dev(K), dev(conf), ts, phase_switch=10, mode=mode)  # infant driver switches at 950
+    xo, To, _ = zo.oil_loop_schedule(W, x0, T0, uv, K, conf.copy(), ts, 10, forward=zo.control_score_forward)
+    assert rel_err(xg.cpu().numpy(), xo) < 1e-4 and rel_err(Tg.cpu().numpy(), To.reshape(64, 3)) < 1e-4
+    p.close()
+
+
 def test_plan_errors(zr, plan17):
     from zedo_release_b200._native import ZedoError
     W = zo.make_weights(seed=0)

@@ -165,3 +165,24 @@ def test_dataset_eval_multi_and_align_to_gt(lib, golden):
     for k in (0, 17, 149):  # incl. the reflected hypothesis (pose 3, hypothesis 2)
         n, s = divmod(k, 5)
         assert np.abs(align_to_gt(g["preds"][n, s], g["gts"][n]) - g["aligned"][k]).max() < 5e-7
+
+
+def test_control_model_through_the_mirror(lib, golden):
+    from lib.algorithms.advanced.control_model import Control_ScoreModelFC_Adv
+    from lib.algorithms.advanced import utils as mutils, sde_lib
+    g = golden("control")
+    W = zo.make_weights(seed=int(g["weights_seed"]), control=True)
+    m = Control_ScoreModelFC_Adv(ref_config(), n_joints=17, joint_dim=3, hidden_dim=1024, embed_dim=512, cond_dim=3)
+    assert set(m.state_dict().keys()) == set(W.keys()) | {"sigmas"}
+    sd = {k: torch.tensor(v) for k, v in W.items()}
+    sd["sigmas"] = m.sigmas.clone()
+    m.load_state_dict(sd)
+    m.to(torch.device("cuda")).eval()
+    x = torch.tensor(g["x"], device="cuda")
+    out = m(x, torch.ones(8, device="cuda") * float(g["t999"]))
+    assert rel_err(out.cpu().numpy(), g["out"]) < 2e-5
+    # callable through get_model_fn (4 arguments), which the shipped reference class is not
+    sde = sde_lib.subVPSDE(beta_min=0.1, beta_max=20.0, N=1000, T=0.1)
+    score = mutils.get_score_fn(sde, m, train=False, continuous=True)(x, torch.ones(8, device="cuda") * 0.05, None, None)
+    ref = -zo.control_score_forward(W, g["x"], np.float32(0.05) * np.float32(999)) / zo.subvp_marginal_std(np.float32(0.05))
+    assert rel_err(score.cpu().numpy(), ref) < 1e-4

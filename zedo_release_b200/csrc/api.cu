@@ -87,7 +87,9 @@ using namespace zedo;
 struct zedo_plan {
   zedo_net_desc desc{};
   int device = 0, num_sms = 148;
-  int D = 0, H = 0, E = 0, L = 0;  // L = rows of the bias table (layers with a time projection)
+  int D = 0, H = 0, E = 0, L = 0;  // L = rows of the per-step bias table
+  int Lt = 0;                      // rows projected from the time embedding (== L for the plain score net)
+  int n_act = 2;                   // blocked activation buffers the program needs
   int64_t cap = 0, m_pad = 0;
 
   // float32 device copies
@@ -118,6 +120,13 @@ struct zedo_plan {
   float* emb = nullptr;
   float* temb = nullptr;
   float* table = nullptr;  // [steps, L, H]
+  float* proj = nullptr;   // control net: [steps, Lt, H] time projections before they are combined into rows
+  float* ubuf = nullptr;   // control net: [steps, H] scratch (U_k)
+  float* sbuf = nullptr;   // control net: [steps, H] running sum of the batch-invariant copy-branch updates
+  // control net constants (float32, device)
+  std::vector<float*> wz2, bz2, gam2c, bet2c;  // per block: zc_b{k}_2 weight/bias, b{k}_gnorm2_copy affine
+  std::vector<float*> static_rows;             // per table row: NULL or a [H] vector broadcast over the steps
+  float* zeros_h = nullptr;
   std::vector<void*> owned;
   // live kernel timing (zedo_plan_profile)
   bool prof_on = false;
@@ -187,6 +196,11 @@ int ensure_tables(zedo_plan* p, int steps) {
   if ((rc = dev_alloc(p, &p->emb, (size_t)steps * p->E))) return rc;
   if ((rc = dev_alloc(p, &p->temb, (size_t)steps * p->E))) return rc;
   if ((rc = dev_alloc(p, &p->table, (size_t)steps * p->L * p->H))) return rc;
+  if (p->desc.kind == ZEDO_NET_CONTROL) {
+    if ((rc = dev_alloc(p, &p->proj, (size_t)steps * p->Lt * p->H))) return rc;
+    if ((rc = dev_alloc(p, &p->ubuf, (size_t)steps * p->H))) return rc;
+    if ((rc = dev_alloc(p, &p->sbuf, (size_t)steps * p->H))) return rc;
+  }
   p->table_steps = steps;
   return 0;
 }
@@ -199,13 +213,53 @@ int build_tables(zedo_plan* p, const float* t999_host, int steps, cudaStream_t s
   if ((rc = launch_timestep_embedding(p->t999_dev, p->freqs, p->emb, steps, p->E / 2, st))) return rc;
   if ((rc = launch_sgemm_tn(p->emb, p->E, p->Ws, p->E, p->bs, p->temb, p->E, steps, p->E, p->E, st))) return rc;
   if ((rc = launch_silu_inplace(p->temb, (int64_t)steps * p->E, st))) return rc;
-  return launch_sgemm_tn(p->temb, p->E, p->Wt_cat, p->E, p->bt_cat, p->table, p->L * p->H, steps, p->L * p->H, p->E,
-                         st);
+  if (p->desc.kind != ZEDO_NET_CONTROL)
+    return launch_sgemm_tn(p->temb, p->E, p->Wt_cat, p->E, p->bt_cat, p->table, p->L * p->H, steps, p->L * p->H,
+                           p->E, st);
+  // ---- Control_ScoreModelFC_Adv (control_model.py:277-382): everything that does not depend on the pose ----
+  // proj rows: P0 pre_dense_t_copy, P1 pre_dense_t, per block k: P(2+4k) dense1_t_copy, P(3+4k) dense1_t,
+  //            P(4+4k) dense2_t, P(5+4k) dense2_t_copy (= U_k)
+  // table rows: R0 = P0 | R1 = b(zc_layer_2) | R2 = P1 | per block: R(3+4k) = P(2+4k) + S_{k-1} W(dense1_copy)^T |
+  //             R(4+4k) = b(zc_b_1) | R(5+4k) = P(3+4k) | R(6+4k) = P(4+4k) + U_k W(zc_b_2)^T + b(zc_b_2)
+  // with S_k = S_{k-1} + SiLU(GN_{gnorm2_copy}(U_k)): the copy branch only ever changes by batch-invariant terms,
+  // because `c = dense2_copy(c)` is overwritten by `c = dense2_t_copy(temb)` (control_model.py:340-341).
+  const int H = p->H, L = p->L, Lt = p->Lt, NB = p->desc.n_blocks;
+  const size_t rowb = (size_t)H * sizeof(float);
+  if ((rc = launch_sgemm_tn(p->temb, p->E, p->Wt_cat, p->E, p->bt_cat, p->proj, Lt * H, steps, Lt * H, p->E, st)))
+    return rc;
+  auto copy_row = [&](int prow, int trow) -> int {
+    ZEDO_CUDA_TRY(cudaMemcpy2DAsync(p->table + (size_t)trow * H, (size_t)L * rowb, p->proj + (size_t)prow * H,
+                                    (size_t)Lt * rowb, rowb, (size_t)steps, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  };
+  for (int r = 0; r < L; ++r)
+    if (p->static_rows[r] != nullptr &&
+        (rc = launch_sgemm_tn(p->temb, p->E, p->Ws, p->E, p->static_rows[r], p->table + (size_t)r * H, L * H, steps, H,
+                              0, st)))
+      return rc;
+  if ((rc = copy_row(0, 0)) || (rc = copy_row(1, 2))) return rc;
+  for (int k = 0; k < NB; ++k) {
+    if ((rc = copy_row(2 + 4 * k, 3 + 4 * k)) || (rc = copy_row(3 + 4 * k, 5 + 4 * k)) ||
+        (rc = copy_row(4 + 4 * k, 6 + 4 * k)))
+      return rc;
+    if (k > 0 && (rc = launch_sgemm_tn(p->sbuf, H, p->w32[3 + 4 * k], H, nullptr, p->table + (size_t)(3 + 4 * k) * H,
+                                       L * H, steps, H, H, st, 1)))
+      return rc;
+    ZEDO_CUDA_TRY(cudaMemcpy2DAsync(p->ubuf, rowb, p->proj + (size_t)(5 + 4 * k) * H, (size_t)Lt * rowb, rowb,
+                                    (size_t)steps, cudaMemcpyDeviceToDevice, st));
+    if ((rc = launch_sgemm_tn(p->ubuf, H, p->wz2[k], H, p->bz2[k], p->table + (size_t)(6 + 4 * k) * H, L * H, steps, H,
+                              H, st, 1)))
+      return rc;
+    if ((rc = launch_gn_silu_rows(p->ubuf, p->zeros_h, nullptr, p->gam2c[k], p->bet2c[k], k > 0 ? p->sbuf : nullptr,
+                                  p->sbuf, steps, H, p->desc.gn_eps, st)))
+      return rc;
+  }
+  return 0;
 }
 
 int ensure_act32(zedo_plan* p) {
   if (!p->act32.empty()) return 0;
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < p->n_act + 1; ++i) {  // last one = raw GEMM output scratch
     float* b = nullptr;
     int rc = dev_alloc(p, &b, (size_t)p->m_pad * p->H);
     if (rc) return rc;
@@ -228,10 +282,15 @@ int net_forward(zedo_plan* p, const float* x, const float* tbl, int64_t B, int m
       const int K = p->w_k[op.weight], N = p->w_n[op.weight];
       if (op.epi == EPI_LINEAR_F32) {
         if ((rc = launch_sgemm_tn(in, K, p->w32[op.weight], K, p->post_bias, p->eps, 64, (int)B, N, K, st))) return rc;
+      } else if (op.epi == EPI_LINEAR_ACT) {
+        if ((rc = launch_sgemm_tn(in, K, p->w32[op.weight], K, tbl + (size_t)op.table_row * p->H,
+                                  p->act32[op.out_buf], p->H, (int)B, N, K, st)))
+          return rc;
       } else {
-        float* raw = p->act32[2];
+        float* raw = p->act32[p->n_act];
         if ((rc = launch_sgemm_tn(in, K, p->w32[op.weight], K, nullptr, raw, p->H, (int)B, N, K, st))) return rc;
-        if ((rc = launch_gn_silu_rows(raw, tbl + (size_t)op.table_row * p->H, nullptr,
+        if ((rc = launch_gn_silu_rows(raw, tbl + (size_t)op.table_row * p->H,
+                                      op.addend_buf >= 0 ? p->act32[op.addend_buf] : nullptr,
                                       p->gamma + (size_t)op.gn * p->H, p->beta + (size_t)op.gn * p->H,
                                       op.resid_buf >= 0 ? p->act32[op.resid_buf] : nullptr, p->act32[op.out_buf], B,
                                       p->H, p->desc.gn_eps, st)))
@@ -320,7 +379,7 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
                      const float* const* tensors, const int64_t* numels, int64_t max_batch, int32_t device) {
   if (!out || !desc || !names || !tensors || !numels) return ZEDO_E_INVALID;
   *out = nullptr;
-  if (desc->kind != ZEDO_NET_SCORE_FC_ADV) return ZEDO_E_SHAPE;  // control net: see DESIGN.md (next)
+  if (desc->kind != ZEDO_NET_SCORE_FC_ADV && desc->kind != ZEDO_NET_CONTROL) return ZEDO_E_INVALID;
   const int D = desc->n_joints * 3, H = desc->hidden, E = desc->embed, NB = desc->n_blocks;
   // GroupNorm(32, hidden): the fused epilogue normalises groups of exactly 32 contiguous channels,
   // i.e. hidden == 1024 -- the only width the reference drivers instantiate (run/opt_main.py:35).
@@ -335,7 +394,6 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
   p->D = D;
   p->H = H;
   p->E = E;
-  p->L = 1 + 2 * NB;
   p->cap = max_batch;
   p->m_pad = round_up(max_batch, 2 * kActTileRows);  // CTA pairs work on 256 rows
   p->use_pairs = !(getenv("ZEDO_TC2") && atoi(getenv("ZEDO_TC2")) == 0);
@@ -364,70 +422,171 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
     if (e != cudaSuccess) PLAN_TRY((int)e);
     tm.t[k] = std::move(v);
   }
-  auto need = [&](const std::string& k, size_t n) -> const std::vector<float>* { return tm.get(k, n); };
-#define NEED(var, key, n)                \
-  const std::vector<float>* var = need(key, n); \
+#define NEED(var, key, n)                              \
+  const std::vector<float>* var = tm.get(key, n);      \
   if (!var) PLAN_TRY(ZEDO_E_MISSING)
 
-  // dense layers in execution order + their time projections
-  std::vector<std::string> dense = {"pre_dense"};
-  std::vector<std::string> gnorm = {"pre_gnorm"};
-  for (int b = 1; b <= NB; ++b) {
-    dense.push_back("b" + std::to_string(b) + "_dense1");
-    dense.push_back("b" + std::to_string(b) + "_dense2");
-    gnorm.push_back("b" + std::to_string(b) + "_gnorm1");
-    gnorm.push_back("b" + std::to_string(b) + "_gnorm2");
-  }
-  std::vector<float> wt_cat((size_t)p->L * H * E), bt_cat((size_t)p->L * H), gam((size_t)p->L * H),
-      bet((size_t)p->L * H);
-  for (int l = 0; l < p->L; ++l) {
-    const int K = l == 0 ? D : H;
-    NEED(w, dense[l] + ".weight", (size_t)H * K);
-    NEED(b, dense[l] + ".bias", (size_t)H);
-    NEED(wt, dense[l] + "_t.weight", (size_t)H * E);
-    NEED(bt, dense[l] + "_t.bias", (size_t)H);
-    NEED(g, gnorm[l] + ".weight", (size_t)H);
-    NEED(be, gnorm[l] + ".bias", (size_t)H);
-    std::memcpy(&wt_cat[(size_t)l * H * E], wt->data(), (size_t)H * E * sizeof(float));
-    for (int i = 0; i < H; ++i) {
-      bt_cat[(size_t)l * H + i] = (*bt)[i] + (*b)[i];
-      gam[(size_t)l * H + i] = (*g)[i];
-      bet[(size_t)l * H + i] = (*be)[i];
-    }
-    PackedWeight pw;
-    PLAN_TRY(pack_weight(w->data(), H, K, 256, &pw));
+  // ---- builders shared by both network kinds -------------------------------------------------------
+  std::vector<float> wt_cat, bt_cat, gam, bet;  // time-projection matrix / bias, GroupNorm affine (per gn index)
+  // a GEMM weight [N, K]: packed for the one-CTA kernel (bn rows per tile), for the CTA-pair kernel when it is
+  // a 1024 x 1024 layer, and kept in float32 for the validation mode; returns its index
+  auto add_weight = [&](const std::string& name, int N, int K, int bn) -> int {
+    const std::vector<float>* w = tm.get(name + ".weight", (size_t)N * K);
+    if (!w) return ZEDO_E_MISSING;
+    PackedWeight pw, pw2;
+    int r = pack_weight(w->data(), N, K, bn, &pw);
+    if (r) return r > 0 ? -1000 - r : r;
     p->owned.push_back(pw.dev);
-    p->packed.push_back(pw);
-    PackedWeight pw2;
-    if (K == H) {
-      PLAN_TRY(pack_weight(w->data(), H, K, 128, &pw2));
+    if (K == H && N == H) {
+      if ((r = pack_weight(w->data(), N, K, 128, &pw2))) return r > 0 ? -1000 - r : r;
       p->owned.push_back(pw2.dev);
     }
-    p->packed_pair.push_back(pw2);
     float* w32 = nullptr;
-    PLAN_TRY(upload(p, &w32, w->data(), w->size()));
+    if ((r = upload(p, &w32, w->data(), w->size()))) return r > 0 ? -1000 - r : r;
+    p->packed.push_back(pw);
+    p->packed_pair.push_back(pw2);
     p->w32.push_back(w32);
-    p->w_n.push_back(H);
+    p->w_n.push_back(N);
     p->w_k.push_back(K);
+    return (int)p->packed.size() - 1;
+  };
+  // one row of the time projection: weight `tname` [H, E]; bias = sum of the listed bias vectors (+ extra)
+  auto add_proj_row = [&](const std::string& tname, std::initializer_list<std::string> biases,
+                          const std::vector<float>* extra) -> int {
+    const std::vector<float>* wt = tm.get(tname + ".weight", (size_t)H * E);
+    if (!wt) return ZEDO_E_MISSING;
+    wt_cat.insert(wt_cat.end(), wt->begin(), wt->end());
+    std::vector<float> b((size_t)H, 0.f);
+    for (const std::string& bn_ : biases) {
+      const std::vector<float>* bv = tm.get(bn_ + ".bias", (size_t)H);
+      if (!bv) return ZEDO_E_MISSING;
+      for (int i = 0; i < H; ++i) b[i] += (*bv)[i];
+    }
+    if (extra)
+      for (int i = 0; i < H; ++i) b[i] += (*extra)[i];
+    bt_cat.insert(bt_cat.end(), b.begin(), b.end());
+    return 0;
+  };
+  auto add_gn = [&](const std::string& name) -> int {
+    const std::vector<float>* g = tm.get(name + ".weight", (size_t)H);
+    const std::vector<float>* b = tm.get(name + ".bias", (size_t)H);
+    if (!g || !b) return ZEDO_E_MISSING;
+    gam.insert(gam.end(), g->begin(), g->end());
+    bet.insert(bet.end(), b->begin(), b->end());
+    return (int)(gam.size() / H) - 1;
+  };
+#define ADD_W(var, name, N, K, bn)                       \
+  const int var = add_weight(name, N, K, bn);            \
+  if (var < 0) PLAN_TRY(var <= -1000 ? -1000 - var : var)
+#define ADD_GN(var, name)          \
+  const int var = add_gn(name);    \
+  if (var < 0) PLAN_TRY(var)
+  auto B_ = [](int b) { return "b" + std::to_string(b); };
+
+  if (desc->kind == ZEDO_NET_SCORE_FC_ADV) {
+    // ScoreModelFC_Adv (model.py:215-298): pre -> [dense1 -> dense2 (+residual)] x NB -> post;
+    // two ping-pong activation buffers; table row l = time projection of layer l (+ both biases)
+    p->L = p->Lt = 1 + 2 * NB;
+    p->n_act = 2;
+    ADD_W(w_pre, "pre_dense", H, D, 256);
+    ADD_GN(g_pre, "pre_gnorm");
+    PLAN_TRY(add_proj_row("pre_dense_t", {"pre_dense_t", "pre_dense"}, nullptr));
+    p->program.push_back({w_pre, -1, 0, 0, g_pre, -1, -1, EPI_GN_SILU});
+    for (int b = 1; b <= NB; ++b) {
+      ADD_W(w1, B_(b) + "_dense1", H, H, 256);
+      ADD_GN(g1, B_(b) + "_gnorm1");
+      PLAN_TRY(add_proj_row(B_(b) + "_dense1_t", {B_(b) + "_dense1_t", B_(b) + "_dense1"}, nullptr));
+      ADD_W(w2, B_(b) + "_dense2", H, H, 256);
+      ADD_GN(g2, B_(b) + "_gnorm2");
+      PLAN_TRY(add_proj_row(B_(b) + "_dense2_t", {B_(b) + "_dense2_t", B_(b) + "_dense2"}, nullptr));
+      p->program.push_back({w1, 0, 1, 2 * b - 1, g1, -1, -1, EPI_GN_SILU});
+      p->program.push_back({w2, 1, 0, 2 * b, g2, 0, -1, EPI_GN_SILU});
+    }
+    ADD_W(w_post, "post_dense", D, H, 64);
+    p->program.push_back({w_post, 0, -1, -1, -1, -1, -1, EPI_LINEAR_F32});
+    p->static_rows.assign((size_t)p->L, nullptr);
+  } else {
+    // Control_ScoreModelFC_Adv (control_model.py:277-382).  Activation buffers: 0 = Pc / CD, 1 = Cact,
+    // 2 = C0 / C1, 3 = h, 4 = h1.  Table/proj row numbering: see build_tables().
+    p->L = 3 + 4 * NB;
+    p->Lt = 2 + 4 * NB;
+    p->n_act = 5;
+    p->static_rows.assign((size_t)p->L, nullptr);
+    // v0 = SiLU(zc_layer_1(infant_cond)) and pre_dense_copy . v0 are pose- and time-invariant: host, once
+    NEED(icond, "infant_cond", (size_t)D);
+    NEED(wz1, "zc_layer_1.weight", (size_t)D * D);
+    NEED(bz1, "zc_layer_1.bias", (size_t)D);
+    NEED(wpdc, "pre_dense_copy.weight", (size_t)H * D);
+    std::vector<float> v0((size_t)D), pdc_v0((size_t)H);
+    for (int i = 0; i < D; ++i) {
+      float a = (*bz1)[i];
+      for (int j = 0; j < D; ++j) a += (*wz1)[(size_t)i * D + j] * (*icond)[j];
+      v0[i] = a / (1.f + expf(-a));
+    }
+    for (int i = 0; i < H; ++i) {
+      float a = 0.f;
+      for (int j = 0; j < D; ++j) a += (*wpdc)[(size_t)i * D + j] * v0[j];
+      pdc_v0[i] = a;
+    }
+    auto static_row = [&](int row, const std::string& bias_name) -> int {
+      const std::vector<float>* bv = tm.get(bias_name + ".bias", (size_t)H);
+      if (!bv) return ZEDO_E_MISSING;
+      return upload(p, &p->static_rows[row], bv->data(), bv->size());
+    };
+    ADD_W(w_pdc, "pre_dense_copy", H, D, 256);
+    ADD_W(w_zc2, "zc_layer_2", H, H, 256);
+    ADD_W(w_pre, "pre_dense", H, D, 256);
+    ADD_GN(g_pc, "pre_gnorm_copy");
+    ADD_GN(g_pre, "pre_gnorm");
+    PLAN_TRY(add_proj_row("pre_dense_t_copy", {"pre_dense_t_copy", "pre_dense_copy"}, &pdc_v0));  // P0
+    PLAN_TRY(add_proj_row("pre_dense_t", {"pre_dense_t", "pre_dense"}, nullptr));                 // P1
+    PLAN_TRY(static_row(1, "zc_layer_2"));
+    p->program.push_back({w_pdc, -1, 0, 0, -1, -1, -1, EPI_LINEAR_ACT});   // Pc   = pre_dense_copy(x + v0) + t-proj
+    p->program.push_back({w_pdc, -1, 1, 0, g_pc, -1, -1, EPI_GN_SILU});    // Cact = SiLU(GN_copy(Pc))
+    p->program.push_back({w_zc2, 0, 2, 1, -1, -1, -1, EPI_LINEAR_ACT});    // C0   = zc_layer_2(Pc)
+    p->program.push_back({w_pre, -1, 3, 2, g_pre, -1, 2, EPI_GN_SILU});    // h    = SiLU(GN(pre_dense(x) + t-proj + C0))
+    for (int b = 1; b <= NB; ++b) {
+      const int k = b - 1;
+      ADD_W(w_d1c, B_(b) + "_dense1_copy", H, H, 256);  // index 3 + 4k (build_tables relies on it)
+      ADD_W(w_zk1, "zc_b" + std::to_string(b) + "_1", H, H, 256);
+      ADD_W(w_d1, B_(b) + "_dense1", H, H, 256);
+      ADD_W(w_d2, B_(b) + "_dense2", H, H, 256);
+      ADD_GN(g1, B_(b) + "_gnorm1");
+      ADD_GN(g2, B_(b) + "_gnorm2");
+      PLAN_TRY(add_proj_row(B_(b) + "_dense1_t_copy", {B_(b) + "_dense1_t_copy", B_(b) + "_dense1_copy"}, nullptr));
+      PLAN_TRY(add_proj_row(B_(b) + "_dense1_t", {B_(b) + "_dense1_t", B_(b) + "_dense1"}, nullptr));
+      PLAN_TRY(add_proj_row(B_(b) + "_dense2_t", {B_(b) + "_dense2_t", B_(b) + "_dense2"}, nullptr));
+      PLAN_TRY(add_proj_row(B_(b) + "_dense2_t_copy", {B_(b) + "_dense2_t_copy"}, nullptr));  // U_k
+      PLAN_TRY(static_row(4 + 4 * k, "zc_b" + std::to_string(b) + "_1"));
+      NEED(wz2, "zc_b" + std::to_string(b) + "_2.weight", (size_t)H * H);
+      NEED(bz2, "zc_b" + std::to_string(b) + "_2.bias", (size_t)H);
+      NEED(g2c, B_(b) + "_gnorm2_copy.weight", (size_t)H);
+      NEED(b2c, B_(b) + "_gnorm2_copy.bias", (size_t)H);
+      float *d_wz2 = nullptr, *d_bz2 = nullptr, *d_g2c = nullptr, *d_b2c = nullptr;
+      PLAN_TRY(upload(p, &d_wz2, wz2->data(), wz2->size()));
+      PLAN_TRY(upload(p, &d_bz2, bz2->data(), bz2->size()));
+      PLAN_TRY(upload(p, &d_g2c, g2c->data(), g2c->size()));
+      PLAN_TRY(upload(p, &d_b2c, b2c->data(), b2c->size()));
+      p->wz2.push_back(d_wz2);
+      p->bz2.push_back(d_bz2);
+      p->gam2c.push_back(d_g2c);
+      p->bet2c.push_back(d_b2c);
+      if (w_d1c != 3 + 4 * k) PLAN_TRY(ZEDO_E_STATE);
+      p->program.push_back({w_d1c, 1, 0, 3 + 4 * k, -1, -1, -1, EPI_LINEAR_ACT});  // CD = dense1_copy(c) + ...
+      p->program.push_back({w_zk1, 0, 2, 4 + 4 * k, -1, -1, -1, EPI_LINEAR_ACT});  // C1 = zc_b_1(CD)
+      p->program.push_back({w_d1, 3, 4, 5 + 4 * k, g1, -1, 2, EPI_GN_SILU});       // h1 = SiLU(GN(dense1(h) + ... + C1))
+      p->program.push_back({w_d2, 4, 3, 6 + 4 * k, g2, 3, -1, EPI_GN_SILU});       // h += SiLU(GN(dense2(h1) + ... + c2))
+    }
+    ADD_W(w_post, "post_dense", D, H, 64);
+    p->program.push_back({w_post, 3, -1, -1, -1, -1, -1, EPI_LINEAR_F32});
+    std::vector<float> z((size_t)H, 0.f);
+    PLAN_TRY(upload(p, &p->zeros_h, z.data(), z.size()));
   }
   {
-    NEED(w, "post_dense.weight", (size_t)D * H);
     NEED(b, "post_dense.bias", (size_t)D);
-    PackedWeight pw;
-    PLAN_TRY(pack_weight(w->data(), D, H, 64, &pw));
-    p->owned.push_back(pw.dev);
-    p->packed.push_back(pw);
-    p->packed_pair.push_back(PackedWeight());
-    float* w32 = nullptr;
-    PLAN_TRY(upload(p, &w32, w->data(), w->size()));
-    p->w32.push_back(w32);
-    p->w_n.push_back(D);
-    p->w_k.push_back(H);
     std::vector<float> pb(64, 0.f);
     for (int i = 0; i < D; ++i) pb[i] = (*b)[i];
     PLAN_TRY(upload(p, &p->post_bias, pb.data(), pb.size()));
-  }
-  {
     NEED(ws, "shared_time_embed.0.weight", (size_t)E * E);
     NEED(bsv, "shared_time_embed.0.bias", (size_t)E);
     PLAN_TRY(upload(p, &p->Ws, ws->data(), ws->size()));
@@ -445,16 +604,9 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
     for (int k = 0; k < half; ++k) fr[k] = expf((float)k * coef);
     PLAN_TRY(upload(p, &p->freqs, fr.data(), fr.size()));
   }
-  // program: pre -> [dense1 -> dense2 (+residual)] x NB -> post; two ping-pong activation buffers
-  p->program.push_back({0, -1, 0, 0, 0, -1, -1, EPI_GN_SILU});
-  for (int b = 0; b < NB; ++b) {
-    p->program.push_back({1 + 2 * b, 0, 1, 1 + 2 * b, 1 + 2 * b, -1, -1, EPI_GN_SILU});
-    p->program.push_back({2 + 2 * b, 1, 0, 2 + 2 * b, 2 + 2 * b, 0, -1, EPI_GN_SILU});
-  }
-  p->program.push_back({p->L, 0, -1, -1, -1, -1, -1, EPI_LINEAR_F32});
   // workspaces
   PLAN_TRY(dev_alloc(p, &p->xa, (size_t)p->m_pad * kBlockK * 2));
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < p->n_act; ++i) {
     __half* a = nullptr;
     PLAN_TRY(dev_alloc(p, &a, (size_t)p->m_pad * H * 2));
     p->act.push_back(a);
@@ -464,6 +616,8 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
   PLAN_TRY(ensure_tables(p, 1));
   ZEDO_CUDA_TRY(cudaDeviceSynchronize());
 #undef NEED
+#undef ADD_W
+#undef ADD_GN
 #undef PLAN_TRY
   *out = p;
   return 0;

@@ -7,13 +7,13 @@
 
 namespace zedo {
 
-// C[M,N] = A[M,K] (row-major, lda) * W[N,K]^T (row-major, ldw) + bias[N] (nullable)
+// C[M,N] (+)= A[M,K] (row-major, lda) * W[N,K]^T (row-major, ldw) + bias[N] (nullable)
 // 64x64 tile, BK = 16, 256 threads, 4x4 outputs per thread.
 constexpr int TS = 64, TK = 16;
 
 __global__ void __launch_bounds__(256)
 sgemm_tn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
-                const float* __restrict__ bias, float* __restrict__ C, int ldc, int M, int N, int K) {
+                const float* __restrict__ bias, float* C, int ldc, int M, int N, int K, int accumulate) {
   __shared__ float As[TK][TS + 1];
   __shared__ float Ws[TK][TS + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -48,7 +48,10 @@ sgemm_tn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int gn = n0 + tx * 4 + j;
-      if (gn < N) C[(int64_t)gm * ldc + gn] = acc[i][j] + (bias ? bias[gn] : 0.f);
+      if (gn < N) {
+        const float prev = accumulate ? C[(int64_t)gm * ldc + gn] : 0.f;
+        C[(int64_t)gm * ldc + gn] = prev + acc[i][j] + (bias ? bias[gn] : 0.f);
+      }
     }
   }
 }
@@ -95,10 +98,10 @@ __global__ void gn_silu_rows_kernel(const float* __restrict__ in, const float* _
 }
 
 int launch_sgemm_tn(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M,
-                    int N, int K, cudaStream_t st) {
+                    int N, int K, cudaStream_t st, int accumulate) {
   if (M == 0 || N == 0) return 0;
   dim3 grid((N + TS - 1) / TS, (M + TS - 1) / TS);
-  sgemm_tn_kernel<<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K);
+  sgemm_tn_kernel<<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K, accumulate);
   ZEDO_LAUNCH_CHECK();
   return 0;
 }

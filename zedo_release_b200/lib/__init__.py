@@ -9,7 +9,7 @@ import importlib
 import sys
 
 _SUBMODULES = ("algorithms", "algorithms.advanced", "algorithms.advanced.sde_lib", "algorithms.advanced.utils",
-               "algorithms.advanced.model", "algorithms.advanced.sampling",
+               "algorithms.advanced.model", "algorithms.advanced.control_model", "algorithms.advanced.sampling",
                "algorithms.advanced.simple_zeroshot_opt", "algorithms.ema", "utils", "utils.transforms",
                "dataset", "dataset.synthetic")
 
