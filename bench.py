@@ -160,11 +160,18 @@ def run_gpu_arm(args):
     import zedo_release_b200 as zr
     from zedo_release_b200 import synthetic as sy
 
-    B, S, J = args.poses, args.hypo, 17
-    cfg = dict(sy.H36M_ZEDO_CFG)
+    B, S, J = args.poses, args.hypo, args.joints
+    base_cfg = {"h36m": sy.H36M_ZEDO_CFG, "pw3d": sy.PW3D_ZEDO_CFG, "mini": sy.MINI_ZEDO_CFG,
+                "syrip": sy.SYRIP_ZEDO_CFG}[args.dataset]
+    cfg = dict(base_cfg)
     cfg["OIL_iterations"] = args.oil_steps
-    ds = sy.make_synthetic_dataset(B, seed=1234 + rank, n_clusters=S)
-    plan = zr.ScorePlan(sy.make_weights(seed=0), n_joints=J, max_batch=B, device=local)
+    infant = args.dataset in ("mini", "syrip")
+    run_kw = dict(phase_switch=int(0.95 * args.oil_steps), ray_init=True, use_conf=False,
+                  pelvis=(0, 3) if args.dataset == "syrip" else (0, 0)) if infant else {}
+    ds = sy.make_synthetic_dataset(B, n_joints=J, seed=1234 + rank, n_clusters=S)
+    control = args.net == "control"
+    plan = zr.ScorePlan(sy.make_weights(seed=0, n_joints=J, control=control), n_joints=J, max_batch=B, device=local,
+                        kind=zr._native.NET_CONTROL if control else zr._native.NET_SCORE_FC_ADV)
     h_db2d = torch.from_numpy(ds["db_2d"]).pin_memory()
     h_K = torch.from_numpy(ds["camera_param"]).pin_memory()
     h_cl = torch.from_numpy(ds["clusters"]).pin_memory()
@@ -173,13 +180,14 @@ def run_gpu_arm(args):
     b_global = B * world  # the IPO loss is a mean over the whole (global) batch (run/opt_main.py:191)
 
     def step_resident():
-        return zr.run_pose_optimisation(plan, d_db2d, d_K, d_cl, cfg, hypo=S, mode=args.mode, b_global=b_global)
+        return zr.run_pose_optimisation(plan, d_db2d, d_K, d_cl, cfg, hypo=S, mode=args.mode, b_global=b_global,
+                                        **run_kw)
 
     def step_e2e():
         a = h_db2d.to(dev, non_blocking=True)
         k = h_K.to(dev, non_blocking=True)
         c = h_cl.to(dev, non_blocking=True)
-        res = zr.run_pose_optimisation(plan, a, k, c, cfg, hypo=S, mode=args.mode, b_global=b_global)
+        res = zr.run_pose_optimisation(plan, a, k, c, cfg, hypo=S, mode=args.mode, b_global=b_global, **run_kw)
         h_out.copy_(res, non_blocking=True)
         return res
 
@@ -249,8 +257,10 @@ def run_gpu_arm(args):
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp16 hi/lo 3-product split on tcgen05, f32 accumulate)"
             if args.mode == "split3" else args.mode, "data": "synthetic",
-            "config": {"workload": f"H36M J=17 hypo={S}, {B} synthetic poses per GPU, random-init concat score net "
-                                   f"(BASELINE configs[1]); {args.oil_steps} OIL steps + 500 IPO iterations per pose",
+            "config": {"workload": f"{args.dataset} J={J} hypo={S}, {B} synthetic poses per GPU, random-init "
+                                   f"{'control (infant)' if control else 'concat'} score net"
+                                   f"{' (BASELINE configs[1])' if (args.dataset, J, S, B, control) == ('h36m', 17, 1, 262144, False) else ''}"
+                                   f"; {args.oil_steps} OIL steps + 500 IPO iterations per pose",
                        "poses_per_gpu": B, "hypotheses": S, "oil_steps": args.oil_steps, "ipo_iterations": 500,
                        "gemm_mode": args.mode, "parallelism": f"pose-sharded x{world}, no data-path collective",
                        "l2": "inputs larger than L2 (2.1 GB of activations per layer pass)"},
@@ -267,7 +277,9 @@ def run_gpu_arm(args):
                          "avg_launch_ms": hid_ms, "launches_timed": hid_n,
                          "other_kernels_ms": {k: v[0] for k, v in prof.items() if k != "hidden_layer"}},
             "oil_pose_steps_per_s": B * world * args.oil_steps * S / (ms_total / args.steps / 1e3),
-            "loop_tflops_algorithmic": FLOP_PER_POSE_STEP * B * world * args.oil_steps * S / (ms_total / args.steps / 1e3) / 1e12,
+            "loop_tflops_algorithmic": (2 * (3 * 3 * J * 1024 + 9 * 1024 * 1024) if control else
+                                        2 * (2 * 3 * J * 1024 + 4 * 1024 * 1024)) * B * world * args.oil_steps * S
+            / (ms_total / args.steps / 1e3) / 1e12,
             "results_finite": finite,
             "cpu_baseline": cpu,
         }
@@ -289,6 +301,10 @@ def main():
     ap.add_argument("--oil-steps", type=int, default=1000, help="OIL steps per pose (reference: 1000)")
     ap.add_argument("--mode", default="split3", choices=["split3", "split2", "fp16", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--dataset", default="h36m", choices=["h36m", "pw3d", "mini", "syrip"],
+                    help="ZeDO config block (IPO key joints / axes / scale clamp; infant configs switch phase at 95%%)")
+    ap.add_argument("--joints", type=int, default=17)
+    ap.add_argument("--net", default="score", choices=["score", "control"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -127,6 +127,15 @@ int zedo_ipo_fit(const float* x0, const float* uv, const float* K, const int32_t
                  int32_t iters, int64_t B_global, float lr, float* R, float* T, float* x_rot,
                  float* qs, int64_t B, int32_t J, void* stream);
 
+/* Infant driver variant (run/opt_main_infant.py:255-300): the pelvis pixel is (uv[pelvis_a] + uv[pelvis_b]) / 2
+ * (joint 0 for Mini-RGBD, joints 0 and 3 for SyRIP) and, when ray_init != 0, x_rot = R . (back-projected 2D rays
+ * scaled so the pelvis ray has length |T|, pelvis-subtracted) instead of R . x0. */
+int zedo_ipo_fit_ex(const float* x0, const float* uv, const float* K, const int32_t* keylist,
+                    int32_t nkey, int32_t axes_mask, int32_t pelvis_a, int32_t pelvis_b,
+                    int32_t ray_init, float ipo_T, float minT, float maxT, int32_t iters,
+                    int64_t B_global, float lr, float* R, float* T, float* x_rot, float* qs, int64_t B,
+                    int32_t J, void* stream);
+
 /* RotOpt.forward / its backward for drivers that keep autograd + torch.optim.Adam
  * (simple_zeroshot_opt.py:20-31).  q [B,4], scale [B], xk [B,nk,3], T0 [B,3], K [B,9];
  * uv_out [B,nk,2].  Backward: d_uv [B,nk,2] -> d_q [B,4], d_scale [B]. */

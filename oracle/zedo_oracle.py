@@ -385,12 +385,28 @@ def quaternion_to_matrix(q):
     return o.reshape(q.shape[:-1] + (3, 3)).astype(f32)
 
 
-def init_translation(key2d, K, ipo_T):
-    """T0 = IPO_T * normalize(K^-1 [u_pelvis, v_pelvis, 1]) (run/opt_main.py:177-179); [B,1,3]."""
+def init_translation(key2d, K, ipo_T, pelvis=(0, 0)):
+    """T0 = IPO_T * normalize(K^-1 [u_pelvis, v_pelvis, 1]) (run/opt_main.py:177-179); [B,1,3].
+    pelvis = (a, b): the pelvis pixel is (key2d[a] + key2d[b]) / 2 -- joint 0, or joints 0 and 3 for
+    SyRIP (run/opt_main_infant.py:259-262)."""
     B = key2d.shape[0]
-    pelvis = np.concatenate([key2d[:, 0, :2].astype(f32), np.ones((B, 1), f32)], axis=-1)
+    pix = ((key2d[:, pelvis[0], :2].astype(f32) + key2d[:, pelvis[1], :2].astype(f32)) / f32(2)).astype(f32)
+    pelvis = np.concatenate([pix, np.ones((B, 1), f32)], axis=-1)
     T = np.einsum("bij,bj->bi", inv3x3(K), pelvis)[:, None, :].astype(f32)
     return (T / np.linalg.norm(T, axis=-1, keepdims=True) * f32(ipo_T)).astype(f32)
+
+
+def ray_init(key2d, K, T, pelvis=(0, 0)):
+    """Infant driver's initial pose (run/opt_main_infant.py:281-292): back-projected 2D rays scaled so
+    the pelvis ray has length |T|, pelvis-subtracted.  key2d [B,J,2], T [B,1,3] -> [B,J,3]."""
+    B, J = key2d.shape[:2]
+    h2d = np.concatenate([key2d.astype(f32), np.ones((B, J, 1), f32)], axis=-1)
+    ray = np.einsum("bij,bnj->bni", inv3x3(K), h2d).astype(f32)
+    root = ((ray[:, pelvis[0]:pelvis[0] + 1] + ray[:, pelvis[1]:pelvis[1] + 1]) / f32(2)).astype(f32)
+    ray = (ray / np.linalg.norm(root, axis=-1, keepdims=True)).astype(f32)
+    ray = (ray * np.linalg.norm(T, axis=-1, keepdims=True)).astype(f32)
+    root = ((ray[:, pelvis[0]:pelvis[0] + 1] + ray[:, pelvis[1]:pelvis[1] + 1]) / f32(2)).astype(f32)
+    return (ray - root).astype(f32)
 
 
 def init_hypothesis(cluster_poses, sid, B):

@@ -294,6 +294,28 @@ def test_ipo_short_trajectory_golden(zr, golden, tag, cfg):
     assert rel_err(T.cpu().numpy(), Tc) < 1e-6
 
 
+@pytest.mark.parametrize("J,pelvis", [(17, (0, 0)), (12, (0, 3))])
+def test_ipo_infant_variants(zr, J, pelvis):
+    """Infant driver (run/opt_main_infant.py:255-300): SyRIP pelvis = mean of joints 0 and 3, and the
+    ray-based initial pose.  With 0 Adam iterations R = I and scale = 1, so x_rot is the ray init itself."""
+    B = 200
+    ds = zo.make_synthetic_dataset(B, n_joints=J, seed=J)
+    uv, K = ds["db_2d"][:, :, :2], ds["camera_param"]
+    x0 = np.zeros((B, J, 3), np.float32)
+    cfg = zo.SYRIP_ZEDO_CFG if J == 12 else zo.MINI_ZEDO_CFG
+    R, T, x_rot, qs = zr.ipo_fit(dev(x0), dev(uv), dev(K), cfg["IPO_keylist"], cfg["RotAxes"], cfg["IPO_T"],
+                                 cfg["IPO_minScaleT"], cfg["IPO_maxScaleT"], iters=0, pelvis=pelvis, ray_init=True)
+    T_o = zo.init_translation(uv, K, cfg["IPO_T"], pelvis=pelvis)
+    assert rel_err(T.cpu().numpy(), T_o.reshape(B, 3)) < 1e-6
+    assert rel_err(x_rot.cpu().numpy(), zo.ray_init(uv, K, T_o, pelvis=pelvis)) < 1e-5
+    assert rel_err(R.cpu().numpy(), np.broadcast_to(np.eye(3, dtype=np.float32), (B, 3, 3))) < 1e-7
+    # after a real fit, x_rot = R . ray_init(T) with the fitted (R, T)
+    R, T, x_rot, qs = zr.ipo_fit(dev(ds["db_3d"]), dev(uv), dev(K), cfg["IPO_keylist"], cfg["RotAxes"], cfg["IPO_T"],
+                                 cfg["IPO_minScaleT"], cfg["IPO_maxScaleT"], iters=30, pelvis=pelvis, ray_init=True)
+    ri = zo.ray_init(uv, K, T.cpu().numpy().reshape(B, 1, 3), pelvis=pelvis)
+    assert rel_err(x_rot.cpu().numpy(), np.einsum("bij,bnj->bni", R.cpu().numpy(), ri)) < 1e-5
+
+
 @pytest.mark.parametrize("axes,nk", [("z", 3), ("xyz", 17), ("y", 12)])
 def test_rotopt_forward_backward_vs_oracle(zr, axes, nk):
     B = 257

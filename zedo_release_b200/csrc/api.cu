@@ -747,12 +747,14 @@ int zedo_oil_loop(zedo_plan* plan, float* x, float* T, const float* uv, const fl
   return 0;
 }
 
-int zedo_ipo_fit(const float* x0, const float* uv, const float* K, const int32_t* keylist, int32_t nkey,
-                 int32_t axes_mask, float ipo_T, float minT, float maxT, int32_t iters, int64_t B_global, float lr,
-                 float* R, float* T, float* x_rot, float* qs, int64_t B, int32_t J, void* stream) {
+int zedo_ipo_fit_ex(const float* x0, const float* uv, const float* K, const int32_t* keylist, int32_t nkey,
+                    int32_t axes_mask, int32_t pelvis_a, int32_t pelvis_b, int32_t ray_init, float ipo_T, float minT,
+                    float maxT, int32_t iters, int64_t B_global, float lr, float* R, float* T, float* x_rot, float* qs,
+                    int64_t B, int32_t J, void* stream) {
   if (B == 0) return 0;
   if (!x0 || !uv || !K || !keylist || !R || !T) return ZEDO_E_INVALID;
-  if (nkey < 1 || nkey > 32 || J < 1 || J > 64 || iters < 0 || iters > 4096 || B < 0 || B_global < 1)
+  if (nkey < 1 || nkey > 32 || J < 1 || J > 64 || iters < 0 || iters > 4096 || B < 0 || B_global < 1 ||
+      pelvis_a < 0 || pelvis_a >= J || pelvis_b < 0 || pelvis_b >= J)
     return ZEDO_E_SHAPE;
   for (int i = 0; i < nkey; ++i)
     if (keylist[i] < 0 || keylist[i] >= J) return ZEDO_E_SHAPE;
@@ -760,10 +762,17 @@ int zedo_ipo_fit(const float* x0, const float* uv, const float* K, const int32_t
   int* kl = nullptr;
   ZEDO_CUDA_TRY(cudaMallocAsync((void**)&kl, (size_t)nkey * sizeof(int), st));
   ZEDO_CUDA_TRY(cudaMemcpyAsync(kl, keylist, (size_t)nkey * sizeof(int), cudaMemcpyHostToDevice, st));
-  int rc = launch_ipo_fit(x0, uv, K, kl, nkey, axes_mask, ipo_T, minT, maxT, iters, B_global, lr, R, T, x_rot, qs, B,
-                          J, st);
+  int rc = launch_ipo_fit(x0, uv, K, kl, nkey, axes_mask, pelvis_a, pelvis_b, ray_init, ipo_T, minT, maxT, iters,
+                          B_global, lr, R, T, x_rot, qs, B, J, st);
   cudaFreeAsync(kl, st);
   return rc;
+}
+
+int zedo_ipo_fit(const float* x0, const float* uv, const float* K, const int32_t* keylist, int32_t nkey,
+                 int32_t axes_mask, float ipo_T, float minT, float maxT, int32_t iters, int64_t B_global, float lr,
+                 float* R, float* T, float* x_rot, float* qs, int64_t B, int32_t J, void* stream) {
+  return zedo_ipo_fit_ex(x0, uv, K, keylist, nkey, axes_mask, 0, 0, 0, ipo_T, minT, maxT, iters, B_global, lr, R, T,
+                         x_rot, qs, B, J, stream);
 }
 
 int zedo_rotopt_forward(const float* q, const float* scale, const float* xk, const float* T0, const float* K,

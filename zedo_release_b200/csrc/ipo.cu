@@ -99,7 +99,8 @@ __device__ __forceinline__ void adam_step(float& p, float g, float& m, float& v,
 
 __global__ void __launch_bounds__(kIpoThreads)
 ipo_fit_kernel(const float* __restrict__ x0, const float* __restrict__ uv, const float* __restrict__ Kmat,
-               const int* __restrict__ keylist, int nk, int axes_mask, float ipo_T, float minT, float maxT, int iters,
+               const int* __restrict__ keylist, int nk, int axes_mask, int pelvis_a, int pelvis_b, int ray_init,
+               float ipo_T, float minT, float maxT, int iters,
                float lam, float lr, float* __restrict__ Rout, float* __restrict__ Tout, float* __restrict__ x_rot,
                float* __restrict__ qs, int64_t B, int J) {
   extern __shared__ float sm[];
@@ -128,8 +129,10 @@ ipo_fit_kernel(const float* __restrict__ x0, const float* __restrict__ uv, const
 #pragma unroll
   for (int i = 0; i < 9; ++i) Km[i] = Kmat[pc * 9 + i];
   inv3x3(Km, Ki);
-  // T0 = IPO_T * normalize(K^-1 [u_pelvis, v_pelvis, 1])   (run/opt_main.py:177-179; joint 0 of uv)
-  const float up = uv[(pc * J) * 2 + 0], vp = uv[(pc * J) * 2 + 1];
+  // T0 = IPO_T * normalize(K^-1 [u_pelvis, v_pelvis, 1])   (run/opt_main.py:177-179).  The pelvis is joint 0, or
+  // the mean of joints 0 and 3 for SyRIP (run/opt_main_infant.py:259-262): (uv[a] + uv[b]) / 2 with a == b allowed.
+  const float up = (uv[(pc * J + pelvis_a) * 2 + 0] + uv[(pc * J + pelvis_b) * 2 + 0]) / 2;
+  const float vp = (uv[(pc * J + pelvis_a) * 2 + 1] + uv[(pc * J + pelvis_b) * 2 + 1]) / 2;
   float T0[3] = {Ki[0] * up + Ki[1] * vp + Ki[2], Ki[3] * up + Ki[4] * vp + Ki[5], Ki[6] * up + Ki[7] * vp + Ki[8]};
   const float tn = sqrtf(T0[0] * T0[0] + T0[1] * T0[1] + T0[2] * T0[2]);
   T0[0] = T0[0] / tn * ipo_T;
@@ -174,7 +177,31 @@ ipo_fit_kernel(const float* __restrict__ x0, const float* __restrict__ uv, const
     qs[pose * 5 + 3] = q.z;
     qs[pose * 5 + 4] = scale;
   }
-  if (x_rot != nullptr) {
+  if (x_rot != nullptr && ray_init) {
+    // infant driver (run/opt_main_infant.py:281-292,300): the hypothesis is replaced by the back-projected 2D
+    // rays, scaled so the pelvis ray has length |T|, pelvis-subtracted, then rotated by the fitted R
+    auto ray = [&](int j, float* r) {
+      const float u = uv[(pose * J + j) * 2 + 0], v = uv[(pose * J + j) * 2 + 1];
+      r[0] = Ki[0] * u + Ki[1] * v + Ki[2];
+      r[1] = Ki[3] * u + Ki[4] * v + Ki[5];
+      r[2] = Ki[6] * u + Ki[7] * v + Ki[8];
+    };
+    float ra[3], rb[3];
+    ray(pelvis_a, ra);
+    ray(pelvis_b, rb);
+    const float root[3] = {(ra[0] + rb[0]) / 2, (ra[1] + rb[1]) / 2, (ra[2] + rb[2]) / 2};
+    const float rn = sqrtf(root[0] * root[0] + root[1] * root[1] + root[2] * root[2]);
+    const float Tn = sqrtf((T0[0] * sc) * (T0[0] * sc) + (T0[1] * sc) * (T0[1] * sc) + (T0[2] * sc) * (T0[2] * sc));
+    for (int j = 0; j < J; ++j) {
+      float rj[3];
+      ray(j, rj);
+      const float a = rj[0] / rn * Tn - root[0] / rn * Tn, b = rj[1] / rn * Tn - root[1] / rn * Tn,
+                  c = rj[2] / rn * Tn - root[2] / rn * Tn;
+      x_rot[(pose * J + j) * 3 + 0] = R[0] * a + R[1] * b + R[2] * c;
+      x_rot[(pose * J + j) * 3 + 1] = R[3] * a + R[4] * b + R[5] * c;
+      x_rot[(pose * J + j) * 3 + 2] = R[6] * a + R[7] * b + R[8] * c;
+    }
+  } else if (x_rot != nullptr) {
     for (int j = 0; j < J; ++j) {  // denoise_x = rot_mat.bmm(x^T)^T   (run/opt_main.py:201)
       const float a = x0[(pose * J + j) * 3 + 0], b = x0[(pose * J + j) * 3 + 1], c = x0[(pose * J + j) * 3 + 2];
       x_rot[(pose * J + j) * 3 + 0] = R[0] * a + R[1] * b + R[2] * c;
@@ -245,7 +272,7 @@ __global__ void rotopt_backward_kernel(const float* __restrict__ q, const float*
 }
 
 int launch_ipo_fit(const float* x0, const float* uv, const float* K, const int* keylist_dev, int nk, int axes_mask,
-                   float ipo_T, float minT, float maxT, int iters, int64_t B_global, float lr, float* R, float* T,
+                   int pelvis_a, int pelvis_b, int ray_init, float ipo_T, float minT, float maxT, int iters, int64_t B_global, float lr, float* R, float* T,
                    float* x_rot, float* qs, int64_t B, int J, cudaStream_t st) {
   if (B == 0) return 0;
   const size_t smem = (size_t)(2 * iters + nk * 5 * kIpoThreads) * sizeof(float);
@@ -254,7 +281,8 @@ int launch_ipo_fit(const float* x0, const float* uv, const float* K, const int* 
     ZEDO_CUDA_TRY(cudaFuncSetAttribute(ipo_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const float lam = (float)(1.0 / ((double)B_global * nk * 2));
   ipo_fit_kernel<<<(unsigned)((B + kIpoThreads - 1) / kIpoThreads), kIpoThreads, smem, st>>>(
-      x0, uv, K, keylist_dev, nk, axes_mask, ipo_T, minT, maxT, iters, lam, lr, R, T, x_rot, qs, B, J);
+      x0, uv, K, keylist_dev, nk, axes_mask, pelvis_a, pelvis_b, ray_init, ipo_T, minT, maxT, iters, lam, lr, R, T,
+      x_rot, qs, B, J);
   ZEDO_LAUNCH_CHECK();
   return 0;
 }

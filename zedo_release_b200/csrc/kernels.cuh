@@ -37,7 +37,7 @@ int launch_gn_silu_rows(const float* in, const float* cbias, const float* addend
                         const float* beta, const float* resid, float* out, int64_t M, int C, float eps,
                         cudaStream_t st);
 int launch_ipo_fit(const float* x0, const float* uv, const float* K, const int* keylist_dev, int nk, int axes_mask,
-                   float ipo_T, float minT, float maxT, int iters, int64_t B_global, float lr, float* R, float* T,
+                   int pelvis_a, int pelvis_b, int ray_init, float ipo_T, float minT, float maxT, int iters, int64_t B_global, float lr, float* R, float* T,
                    float* x_rot, float* qs, int64_t B, int J, cudaStream_t st);
 int launch_rotopt_forward(const float* q, const float* scale, const float* xk, const float* T0, const float* K,
                           float minT, float maxT, float* uv_out, int64_t B, int nk, cudaStream_t st);

@@ -166,8 +166,10 @@ def axes_mask(rot_axes: str) -> int:
 
 # -- IPO (run/opt_main.py:175-201) ------------------------------------------------------------------------
 def ipo_fit(x0: torch.Tensor, uv: torch.Tensor, K: torch.Tensor, keylist: Sequence[int], rot_axes: str, ipo_T: float,
-            minT: float, maxT: float, iters: int = 500, b_global: Optional[int] = None, lr: float = 0.1):
-    """Returns (R [B,3,3], T [B,3], x_rot [B,J,3], qs [B,5])."""
+            minT: float, maxT: float, iters: int = 500, b_global: Optional[int] = None, lr: float = 0.1,
+            pelvis: Tuple[int, int] = (0, 0), ray_init: bool = False):
+    """Returns (R [B,3,3], T [B,3], x_rot [B,J,3], qs [B,5]).  ``pelvis`` / ``ray_init``: the infant
+    driver's variants (run/opt_main_infant.py:255-300; SyRIP pelvis = mean of joints 0 and 3)."""
     x0, uv, K = _f32(x0, "x0"), _f32(uv, "uv"), _f32(K, "K")
     B, J = x0.shape[0], x0.shape[1]
     dev = x0.device
@@ -176,9 +178,10 @@ def ipo_fit(x0: torch.Tensor, uv: torch.Tensor, K: torch.Tensor, keylist: Sequen
     x_rot = torch.empty_like(x0)
     qs = torch.empty((B, 5), dtype=torch.float32, device=dev)
     kl = nat.i32_array(keylist)
-    nat.check(nat.lib.zedo_ipo_fit(_ptr(x0), _ptr(uv), _ptr(K), kl, len(kl), axes_mask(rot_axes), float(ipo_T),
-                                   float(minT), float(maxT), int(iters), int(b_global if b_global else B), float(lr),
-                                   _ptr(R), _ptr(T), _ptr(x_rot), _ptr(qs), B, J, _stream()), "zedo_ipo_fit")
+    nat.check(nat.lib.zedo_ipo_fit_ex(_ptr(x0), _ptr(uv), _ptr(K), kl, len(kl), axes_mask(rot_axes), int(pelvis[0]),
+                                      int(pelvis[1]), int(bool(ray_init)), float(ipo_T), float(minT), float(maxT),
+                                      int(iters), int(b_global if b_global else B), float(lr), _ptr(R), _ptr(T),
+                                      _ptr(x_rot), _ptr(qs), B, J, _stream()), "zedo_ipo_fit_ex")
     return R, T, x_rot, qs
 
 
@@ -249,10 +252,14 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
 # -- the whole per-hypothesis pipeline (run/opt_main.py:166-222) ------------------------------------------
 def run_pose_optimisation(plan: ScorePlan, db_2d: torch.Tensor, K: torch.Tensor, clusters: torch.Tensor, cfg: dict,
                           hypo: int = 1, mode="split3", t_start: float = 0.1, b_global: Optional[int] = None,
-                          steps: Optional[int] = None) -> torch.Tensor:
+                          steps: Optional[int] = None, phase_switch: Optional[int] = None,
+                          pelvis: Tuple[int, int] = (0, 0), ray_init: bool = False, use_conf: bool = True
+                          ) -> torch.Tensor:
     """db_2d [B,J,3] = (u,v,conf), K [B,3,3], clusters [S,J,3] (cluster file content).
     Returns batch_results [B, hypo, J, 3] (the array run/opt_main.py:224 hands to eval_multi).
     ``b_global``: batch size of the IPO loss mean when the poses are a shard of a larger batch.
+    Infant driver (run/opt_main_infant.py): ``phase_switch=950``, ``ray_init=True``, ``use_conf=False``,
+    ``pelvis=(0, 3)`` for SyRIP.
     """
     db_2d, K, clusters = _f32(db_2d, "db_2d"), _f32(K, "K"), _f32(clusters, "clusters")
     B, J = db_2d.shape[0], db_2d.shape[1]
@@ -262,10 +269,12 @@ def run_pose_optimisation(plan: ScorePlan, db_2d: torch.Tensor, K: torch.Tensor,
     rel = (clusters - clusters[:, 0:1, :]).contiguous()
     out = torch.empty((B, hypo, J, 3), dtype=torch.float32, device=db_2d.device)
     for sid in range(hypo):
-        conf = db_2d[:, :, 2].contiguous()  # re-read per hypothesis like opt_main.py:171
+        conf = db_2d[:, :, 2].contiguous() if use_conf else None  # re-read per hypothesis like opt_main.py:171
         x0 = rel[sid:sid + 1].expand(B, J, 3).contiguous()
         _, T, x, _ = ipo_fit(x0, uv, K, cfg["IPO_keylist"], cfg["RotAxes"], cfg["IPO_T"], cfg["IPO_minScaleT"],
-                             cfg["IPO_maxScaleT"], cfg["IPO_iterations"], b_global=b_global)
-        plan.oil_loop(x, T, uv, K, conf, ts, phase_switch=n_steps // 5, mode=mode)
+                             cfg["IPO_maxScaleT"], cfg["IPO_iterations"], b_global=b_global, pelvis=pelvis,
+                             ray_init=ray_init)
+        plan.oil_loop(x, T, uv, K, conf, ts, phase_switch=n_steps // 5 if phase_switch is None else phase_switch,
+                      mode=mode)
         out[:, sid] = x
     return out
