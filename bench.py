@@ -170,7 +170,9 @@ def run_gpu_arm(args):
                   pelvis=(0, 3) if args.dataset == "syrip" else (0, 0)) if infant else {}
     ds = sy.make_synthetic_dataset(B, n_joints=J, seed=1234 + rank, n_clusters=S)
     control = args.net == "control"
-    plan = zr.ScorePlan(sy.make_weights(seed=0, n_joints=J, control=control), n_joints=J, max_batch=B, device=local,
+    # hypotheses are stacked along the batch axis when the plan has room (up to ~512k rows = 4.3 GB of activations)
+    cap = B * max(1, min(S, 524288 // B))
+    plan = zr.ScorePlan(sy.make_weights(seed=0, n_joints=J, control=control), n_joints=J, max_batch=cap, device=local,
                         kind=zr._native.NET_CONTROL if control else zr._native.NET_SCORE_FC_ADV)
     h_db2d = torch.from_numpy(ds["db_2d"]).pin_memory()
     h_K = torch.from_numpy(ds["camera_param"]).pin_memory()

@@ -395,3 +395,48 @@ def test_pipeline_shapes_and_quality(zr, plan17):
     e2, i2 = zr.eval_multi(res, dev(ds["db_3d"], torch.float64), protocol2=True)
     assert (e2 <= e1 + 1e-12).all()  # Procrustes alignment never increases the error
     assert set(i1.cpu().numpy().tolist()) <= {0, 1}
+
+
+def test_hypothesis_batching_is_exact(zr, plan17):
+    """Stacking hypotheses along the batch axis (one IPO kernel + one OIL loop for a group) gives bit-identical
+    results to running them one by one, like the reference's `for sid in range(args.hypo)` loop."""
+    B, S = 300, 5
+    ds = zo.make_synthetic_dataset(B, seed=31, n_clusters=S)
+    cfg = dict(zo.H36M_ZEDO_CFG)
+    args = (dev(ds["db_2d"]), dev(ds["camera_param"]), dev(ds["clusters"]), cfg)
+    stacked = zr.run_pose_optimisation(plan17, *args, hypo=S, steps=12)  # capacity 4096 -> all 5 in one pass
+    small = zr.ScorePlan(zo.make_weights(seed=0), n_joints=17, max_batch=B, device=0)  # capacity 300 -> one by one
+    serial = zr.run_pose_optimisation(small, *args, hypo=S, steps=12)
+    small.close()
+    assert torch.equal(stacked, serial)
+    # and each hypothesis really starts from its own cluster pose
+    assert not torch.equal(stacked[:, 0], stacked[:, 1])
+
+
+def test_full_size_batch_properties(zr):
+    """BASELINE configs[1] size (262,144 poses): sampled rows of the tcgen05 forward against the oracle, and a
+    3-step OIL loop on the full batch equals the same rows run on their own (row independence, bit-exact)."""
+    B = 262144
+    W = zo.make_weights(seed=0)
+    p = zr.ScorePlan(W, n_joints=17, max_batch=B, device=0)
+    rng = np.random.default_rng(7)
+    ds = zo.make_synthetic_dataset(4096, seed=11)
+    rep = B // 4096
+    x = np.tile(ds["db_3d"], (rep, 1, 1)).astype(np.float32) + rng.normal(0, 0.02, (B, 17, 3)).astype(np.float32)
+    xg = dev(x)
+    out = p.forward(xg, 55.5, mode="split3")
+    assert torch.isfinite(out).all()
+    rows = rng.choice(B, 256, replace=False)
+    ref = zo.score_forward(W, x[rows], np.float32(55.5))
+    assert rel_err(out[rows].cpu().numpy(), ref) < 2e-5
+    uv, K, conf = (dev(np.tile(ds[k], (rep, 1, 1))) for k in ("db_2d", "camera_param", "db_2d"))
+    uv, conf = uv[:, :, :2].contiguous(), conf[:, :, 2].contiguous()
+    T = dev(np.tile(zo.init_translation(ds["db_2d"][:, :, :2], ds["camera_param"], 3.0).reshape(4096, 3), (rep, 1)))
+    ts = zo.oil_time_grid()[199:202]
+    xa, Ta = xg.clone(), T.clone()
+    p.oil_loop(xa, Ta, uv, K, conf.clone(), ts, phase_switch=1)
+    sel = torch.tensor(np.sort(rows), device="cuda")
+    xb, Tb = xg[sel].clone(), T[sel].clone()
+    p.oil_loop(xb, Tb, uv[sel].contiguous(), K[sel].contiguous(), conf[sel].clone(), ts, phase_switch=1)
+    assert torch.equal(xa[sel], xb) and torch.equal(Ta[sel], Tb)
+    p.close()

@@ -268,13 +268,23 @@ def run_pose_optimisation(plan: ScorePlan, db_2d: torch.Tensor, K: torch.Tensor,
     ts = linspace_schedule(t_start, float(cfg["sampling_eps"]), n_steps)
     rel = (clusters - clusters[:, 0:1, :]).contiguous()
     out = torch.empty((B, hypo, J, 3), dtype=torch.float32, device=db_2d.device)
-    for sid in range(hypo):
-        conf = db_2d[:, :, 2].contiguous() if use_conf else None  # re-read per hypothesis like opt_main.py:171
-        x0 = rel[sid:sid + 1].expand(B, J, 3).contiguous()
-        _, T, x, _ = ipo_fit(x0, uv, K, cfg["IPO_keylist"], cfg["RotAxes"], cfg["IPO_T"], cfg["IPO_minScaleT"],
-                             cfg["IPO_maxScaleT"], cfg["IPO_iterations"], b_global=b_global, pelvis=pelvis,
-                             ray_init=ray_init)
-        plan.oil_loop(x, T, uv, K, conf, ts, phase_switch=n_steps // 5 if phase_switch is None else phase_switch,
+    # Hypotheses are independent runs of the same loop (opt_main.py:166): as many as fit the plan are stacked
+    # along the batch axis (row = h * B + pose) so one IPO kernel and one OIL loop serve the whole group.
+    group = max(1, min(hypo, plan.capacity // max(B, 1)))
+    if B > plan.capacity:
+        raise ValueError(f"batch of {B} poses exceeds the plan capacity {plan.capacity}")
+    conf0 = db_2d[:, :, 2].contiguous() if use_conf else None
+    for sid in range(0, hypo, group):
+        g = min(group, hypo - sid)
+        x0 = rel[sid:sid + g].unsqueeze(1).expand(g, B, J, 3).reshape(g * B, J, 3).contiguous()
+        uv_g = uv.repeat(g, 1, 1) if g > 1 else uv
+        K_g = K.repeat(g, 1, 1) if g > 1 else K
+        # conf is re-read from the dataset for every hypothesis (opt_main.py:171) and clamped in place per run
+        conf = None if conf0 is None else (conf0.repeat(g, 1) if g > 1 else conf0.clone())
+        _, T, x, _ = ipo_fit(x0, uv_g, K_g, cfg["IPO_keylist"], cfg["RotAxes"], cfg["IPO_T"], cfg["IPO_minScaleT"],
+                             cfg["IPO_maxScaleT"], cfg["IPO_iterations"], b_global=b_global if b_global else B,
+                             pelvis=pelvis, ray_init=ray_init)
+        plan.oil_loop(x, T, uv_g, K_g, conf, ts, phase_switch=n_steps // 5 if phase_switch is None else phase_switch,
                       mode=mode)
-        out[:, sid] = x
+        out[:, sid:sid + g] = x.reshape(g, B, J, 3).transpose(0, 1)
     return out
