@@ -38,8 +38,8 @@ struct TileCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int NPROD, int EPI>
-__global__ void __launch_bounds__(kTcThreads, 1) layer_tc_kernel(const LayerArgs args) {
+template <int BN, int NPROD, int EPI, int EW>
+__global__ void __launch_bounds__(tc_threads(EW), 1) layer_tc_kernel(const LayerArgs args) {
   using Cfg = TileCfg<BN, NPROD>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) layer_tc_kernel(const LayerArgs
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], kEpiWarps * 32);
+      mbar_init(&tmem_empty[i], EW * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) layer_tc_kernel(const LayerArgs
   } else {
     // ===================== epilogue: thread = one row x half of the tile's columns =====================
     const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int chalf = (warp - 2) >> 2;  // which half of the BN columns
+    const int chalf = (warp - 2) >> 2;  // which slice of the BN columns
     const int r = q * 32 + lane;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) layer_tc_kernel(const LayerArgs
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      epilogue_tile<BN, EPI>(args, tmem_base + (uint32_t)(as * BN), q, chalf, r, mt, nt);
+      epilogue_tile<BN, EPI, EW>(args, tmem_base + (uint32_t)(as * BN), q, chalf, r, mt, nt);
       tc_fence_before();
       mbar_arrive(&tmem_empty[as]);
     }
@@ -184,11 +184,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) layer_tc_kernel(const LayerArgs
 
 // ---- host launcher ------------------------------------------------------------------------------------
 
-template <int BN, int NPROD, int EPI>
-static int launch_one(const LayerArgs& a, int num_sms, cudaStream_t st) {
+template <int BN, int NPROD, int EPI, int EW>
+static int launch_ew(const LayerArgs& a, int num_sms, cudaStream_t st) {
   using Cfg = TileCfg<BN, NPROD>;
   static bool configured = false;
-  auto kern = layer_tc_kernel<BN, NPROD, EPI>;
+  auto kern = layer_tc_kernel<BN, NPROD, EPI, EW>;
   if (!configured) {
     ZEDO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
@@ -196,9 +196,17 @@ static int launch_one(const LayerArgs& a, int num_sms, cudaStream_t st) {
   const int tiles = a.m_tiles * a.n_tiles;
   if (tiles == 0) return 0;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(a);
+  kern<<<grid, tc_threads(EW), Cfg::kSmemBytes, st>>>(a);
   ZEDO_LAUNCH_CHECK();
   return 0;
+}
+
+template <int BN, int NPROD, int EPI>
+static int launch_one(const LayerArgs& a, int num_sms, cudaStream_t st) {
+  if constexpr (BN >= 256) {
+    if (epi_warps_from_env(BN) == 16) return launch_ew<BN, NPROD, EPI, 16>(a, num_sms, st);
+  }
+  return launch_ew<BN, NPROD, EPI, 8>(a, num_sms, st);
 }
 
 template <int BN, int EPI>

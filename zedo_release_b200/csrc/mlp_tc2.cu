@@ -13,7 +13,7 @@
 //   peer_full[s]  leader only: the peer's relay lane observed its full[s] and arrived remotely
 //   empty[s]      tcgen05.commit multicast (mask 0b11): the MMAs that read stage s in BOTH CTAs retired
 //   tmem_full[a]  tcgen05.commit multicast: accumulator a complete in both TMEMs
-//   tmem_empty[a] leader only, count 16: one arrive per epilogue warp of both CTAs (peer: remote)
+//   tmem_empty[a] leader only, count 2*EW: one arrive per epilogue warp of both CTAs (peer: remote)
 #include <cstdlib>
 
 #include "tc_common.cuh"
@@ -64,8 +64,9 @@ struct PairCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
-template <int NPROD, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) layer_tc2_kernel(const LayerArgs args) {
+template <int NPROD, int EPI, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc_threads(EW), 1)
+layer_tc2_kernel(const LayerArgs args) {
   using Cfg = PairCfg<NPROD>;
   constexpr int S = Cfg::kStages;
   constexpr int BN = Cfg::kBN;
@@ -94,7 +95,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) layer
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 2 * kEpiWarps);
+      mbar_init(&tmem_empty[i], 2 * EW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -206,7 +207,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) layer
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      epilogue_tile<BN, EPI>(args, tmem_base + (uint32_t)(as * BN), q, chalf, r, mt, nt);
+      epilogue_tile<BN, EPI, EW>(args, tmem_base + (uint32_t)(as * BN), q, chalf, r, mt, nt);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[as], 0);  // the leader's MMA lane owns accumulator reuse
@@ -222,11 +223,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) layer
   }
 }
 
-template <int NPROD, int EPI>
-static int launch_pair(const LayerArgs& a, int num_sms, cudaStream_t st) {
+template <int NPROD, int EPI, int EW>
+static int launch_pair_ew(const LayerArgs& a, int num_sms, cudaStream_t st) {
   using Cfg = PairCfg<NPROD>;
   static bool configured = false;
-  auto kern = layer_tc2_kernel<NPROD, EPI>;
+  auto kern = layer_tc2_kernel<NPROD, EPI, EW>;
   if (!configured) {
     ZEDO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
@@ -236,9 +237,15 @@ static int launch_pair(const LayerArgs& a, int num_sms, cudaStream_t st) {
   if (pairs == 0) return 0;
   const int max_pairs = num_sms / 2;
   const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
-  kern<<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(a);
+  kern<<<grid, tc_threads(EW), Cfg::kSmemBytes, st>>>(a);
   ZEDO_LAUNCH_CHECK();
   return 0;
+}
+
+template <int NPROD, int EPI>
+static int launch_pair(const LayerArgs& a, int num_sms, cudaStream_t st) {
+  return epi_warps_from_env(256) == 16 ? launch_pair_ew<NPROD, EPI, 16>(a, num_sms, st)
+                                       : launch_pair_ew<NPROD, EPI, 8>(a, num_sms, st);
 }
 
 template <int EPI>

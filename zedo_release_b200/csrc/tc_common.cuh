@@ -1,6 +1,8 @@
 // Shared device code of the tcgen05 layer kernels (mlp_tc.cu: one CTA per tile; mlp_tc2.cu: CTA pairs
 // with cta_group::2): PTX wrappers, descriptors and the fused epilogue.
 #pragma once
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace zedo {
@@ -158,16 +160,21 @@ __device__ __forceinline__ void add_hi_lo(float* v, const uint4& h4, const uint4
 }
 
 
-constexpr int kEpiWarps = 8;                     // two warps per TMEM lane quarter, each owns half the columns
-constexpr int kTcThreads = 64 + kEpiWarps * 32;  // producer warp + MMA warp + epilogue warps
+// EW epilogue warps per CTA (8 or 16): EW/4 warps share a TMEM lane quarter and split the tile's columns
+constexpr int tc_threads(int ew) { return 64 + ew * 32; }  // producer warp + MMA warp + epilogue warps
+inline int epi_warps_from_env(int bn) {
+  static const int v = getenv("ZEDO_EW") ? atoi(getenv("ZEDO_EW")) : 8;  // 16 measured slower (96-register cap, r01)
+  return (bn >= 256 && v == 16) ? 16 : 8;
+}
 
 // Fused epilogue of one 128 x BN tile for one thread (= one row x half of the columns):
 // accumulator * descale + per-column constant (+ addend) -> GroupNorm(32) -> SiLU (+ residual) -> hi/lo split
 // -> blocked store; or the float32 store of post_dense.  tmem_acc = TMEM address of the accumulator stage.
-template <int BN, int EPI>
+template <int BN, int EPI, int EW>
 __device__ __forceinline__ void epilogue_tile(const LayerArgs& args, uint32_t tmem_acc, int q, int chalf, int r,
                                               int mt, int nt) {
-  constexpr int kGroupsPerWarp = BN / 64;
+  constexpr int kGroupsPerWarp = (BN / 32) / (EW / 4);
+  static_assert(kGroupsPerWarp >= 1, "too many epilogue warps for this tile width");
   const int n_total = args.n_tiles * BN;
   const int nkb_out = n_total / kBlockK;
   constexpr int64_t kLoOff = kActTileRows * kBlockK;
