@@ -270,7 +270,7 @@ def run_gpu_arm(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "layer_tc_kernel<256,3,GN_SILU> (1024x1024 hidden layer)",
+            "roofline": {"bound": "tensor", "kernel": "layer_tc2_kernel<3,GN_SILU> (1024x1024 hidden layer, tcgen05 cta_group::2)",
                          "achieved": achieved_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": (achieved_tflops / peaks["tflops"]) if achieved_tflops else None,
                          "traffic": ncu_traffic, "peak_source": peaks["src"],

@@ -60,12 +60,14 @@ if os.path.exists(rp):
                     d[w] = r[idx[w]]
         caps.append(d)
     summary["layer_kernel_captures"] = caps
-    hid = [c for c in caps if "256, 3, 0" in c.get("Kernel Name", "")]
+    hid = [c for c in caps if "layer_tc2_kernel" in c.get("Kernel Name", "")]
+    if not hid:
+        hid = [c for c in caps if "256, 3, 0" in c.get("Kernel Name", "")]
     if hid:
         summary["hidden_layer_dram_bytes_per_launch"] = sum(c["dram__bytes_read.sum"] + c["dram__bytes_write.sum"] for c in hid) / len(hid)
         summary["hidden_layer_tensor_pipe_active_pct"] = sum(c["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"] for c in hid) / len(hid)
     with open(os.path.join(out_dir, f"{tag}_layer_kernel_ncu.md"), "w") as f:
-        f.write(f"# ncu --set full, layer_tc_kernel ({tag})\n\n`ncu --set full --clock-control none --import-source on -k regex:layer_tc_kernel` "
+        f.write(f"# ncu --set full, layer_tc_kernel ({tag})\n\n`ncu --set full --clock-control none --import-source on -k regex:layer_tc` "
                 "on 262,144 poses.  One row per captured launch.\n\n")
         keys = [w for w in want if w in idx]
         f.write("| " + " | ".join(keys) + " |\n|" + "---|" * len(keys) + "\n")
