@@ -158,6 +158,13 @@ int zedo_eval_multi(const float* pred, const double* gt, int32_t protocol2, int6
                     int32_t J, const int32_t* joint_subset, int32_t n_sub, double* err_min,
                     int32_t* argmin, double* err_all, double* aligned, void* stream);
 
+/* PCK / AUC of MPI-INF-3DHP.  Replaces: compute_PCK / compute_AUC (lib/algorithms/advanced/utils.py:814-849,
+ * called from lib/dataset/mpii3dHP.py:480-481) on the selected hypothesis select[n] (NULL = hypothesis 0).
+ * counts: device uint64[31], counts[k] = number of (pose, joint) with error_mm < 5 k (thresholds
+ * linspace(0, 150, 31)); PCK = 100 counts[30] / total, AUC = mean_k 100 counts[k] / total. */
+int zedo_pck_counts(const float* pred, const double* gt, const int32_t* select, int64_t N, int32_t S,
+                    int32_t J, const int32_t* joint_subset, int32_t n_sub, uint64_t* counts, void* stream);
+
 /* ---- misc ---------------------------------------------------------------------------------------- */
 const char* zedo_strerror(int code);
 int zedo_abi_version(void);

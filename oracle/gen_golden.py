@@ -422,6 +422,13 @@ def main():
         ev[f"agg_p{int(p2)}"] = np.float64(e_ref)
         ev[f"min_p{int(p2)}"] = np.array(res_ref)
         ev[f"idx_p{int(p2)}"] = np.array(idx_ref)
+    sel = np.array(ev["idx_p0"])
+    min_pred = preds[np.arange(N), sel]
+    pck_ref = R.mutils.compute_PCK(preds=min_pred.reshape((-1, 17, 3)), gts=gts)
+    auc_ref = R.mutils.compute_AUC(preds=min_pred.reshape((-1, 17, 3)), gts=gts)
+    ck.check("compute_PCK", zo.compute_pck(gts, min_pred), pck_ref, 1e-12)
+    ck.check("compute_AUC", zo.compute_auc(gts, min_pred), auc_ref, 1e-12)
+    ev["pck"], ev["auc"] = np.float64(pck_ref), np.float64(auc_ref)
     pw = R.PW3D.__new__(R.PW3D)
     pw.db_3d = gts
     with redirect_stdout(io.StringIO()):

@@ -595,6 +595,19 @@ def mpjpe(pred, gt):
     return np.mean(np.sqrt(np.square(pred - gt).sum(axis=1)))
 
 
+def compute_pck(gts, preds, eval_joints=None, threshold=150):
+    """``compute_PCK`` (utils.py:814-834): % of joints whose error (mm, scale 1000) is < threshold."""
+    if eval_joints is None:
+        eval_joints = list(range(gts.shape[1]))
+    err = np.sqrt(np.sum(np.power(preds - gts, 2), axis=2))[:, eval_joints] * 1000
+    return float((err < threshold).sum() / err.size) * 100
+
+
+def compute_auc(gts, preds, eval_joints=None):
+    """``compute_AUC`` (utils.py:837-848): mean PCK over thresholds linspace(0, 150, 31)."""
+    return float(np.mean([compute_pck(gts, preds, eval_joints, t) for t in np.linspace(0, 150, 31)]))
+
+
 def eval_multi(preds, gts, protocol2=False, actions=None, joint_subset=None):
     """Multi-hypothesis evaluation (h36m.py:365-442; pw3d.py:286-345 for the plain mean).
 

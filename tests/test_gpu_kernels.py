@@ -361,6 +361,20 @@ def test_eval_multi_golden(zr, golden):
     assert abs(zr.aggregate_errors(zr.eval_multi(pred, gt, protocol2=True)[0]) - float(g["agg_pw3d_p1"])) < 2e-7
 
 
+def test_pck_auc_golden(zr, golden):
+    """3DHP PCK / AUC (utils.py:814-849) of the selected hypotheses, against the reference's own numbers."""
+    g = golden("eval")
+    pred, gt = dev(g["preds"]), dev(g["gts"], torch.float64)
+    _, idx = zr.eval_multi(pred, gt, protocol2=False)
+    pck, auc = zr.pck_auc(pred, gt, select=idx)
+    assert abs(pck - float(g["pck"])) < 1e-9 and abs(auc - float(g["auc"])) < 1e-9
+    sub = [1, 2, 3, 4, 5, 6, 8, 10, 11, 12, 13, 14]
+    sel = idx.cpu().numpy()
+    mp = g["preds"][np.arange(30), sel]
+    pck_s, auc_s = zr.pck_auc(pred, gt, select=idx, joint_subset=sub)
+    assert abs(pck_s - zo.compute_pck(g["gts"], mp, sub)) < 1e-9 and abs(auc_s - zo.compute_auc(g["gts"], mp, sub)) < 1e-9
+
+
 def test_eval_multi_large_random_and_subset(zr):
     rng = np.random.default_rng(0)
     N, S, J = 500, 7, 17

@@ -130,3 +130,6 @@ def test_procrustes_and_eval_multi(golden):
     assert g["idx_p0"][5] == 0  # exact tie -> first index wins
     agg, _, _ = zo.eval_multi(preds, gts, protocol2=True)
     assert abs(agg - float(g["agg_pw3d_p1"])) < 1e-12
+    min_pred = preds[np.arange(N), g["idx_p0"]]
+    assert abs(zo.compute_pck(gts, min_pred) - float(g["pck"])) < 1e-12
+    assert abs(zo.compute_auc(gts, min_pred) - float(g["auc"])) < 1e-12

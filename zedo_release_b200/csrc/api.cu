@@ -719,31 +719,39 @@ int zedo_oil_loop(zedo_plan* plan, float* x, float* T, const float* uv, const fl
   if ((rc = build_tables(plan, t999.data(), steps, st))) return rc;
   // the pageable t999 buffer has been consumed by the (staged) async copy once the call returns
   const bool tc = gemm_mode != ZEDO_GEMM_FP32;
+  // Step i = geometry(i) -> network(i) -> predictor update(i).  The update of step i is fused into the geometry
+  // kernel of step i+1 (same float32 ops; x makes one HBM round trip per step instead of two); the last step's
+  // update runs as its own kernel.  A requested dump of step i is written by whichever kernel applies update i.
   int next_dump = 0;
+  SdeCoef prev{};
   for (int i = 0; i < steps; ++i) {
-    // gradient_field_gen + `denoise_x += joint_gradient` (opt_main.py:203-208); conf is clamped in
-    // place by the first call of the reference and stays clamped
+    float* dump_ptr = nullptr;
+    if (i > 0 && next_dump < n_dump && dump_steps[next_dump] == i - 1) {
+      dump_ptr = dump + (size_t)next_dump * B * D;
+      ++next_dump;
+      while (next_dump < n_dump && dump_steps[next_dump] == i - 1) ++next_dump;  // duplicates: first slot only
+    }
     {
+      // gradient_field_gen + `denoise_x += joint_gradient` (opt_main.py:203-208); conf is clamped in place by
+      // the first call of the reference and stays clamped
       ProfScope ps(plan, 3, st);
       rc = launch_grad_field(uv, x, K, conf, T, i >= phase_switch ? 1 : 0, i == 0 ? 1 : 0, nullptr, x,
-                             tc ? plan->xa : nullptr, B, J, st);
+                             tc ? plan->xa : nullptr, B, J, st, i > 0 ? plan->eps : nullptr, &prev, dump_ptr);
     }
     if (rc) return rc;
     const float* tbl = plan->table + (size_t)i * plan->L * plan->H;
     if ((rc = net_forward(plan, x, tbl, B, gemm_mode, tc, st))) return rc;
-    const SdeCoef c = subvp_coef(t_sched[i], beta_min, beta_max, n_scales);
-    // pc_sampler with probability_flow=True, noise_removal=True returns x_mean (sampling.py:524-527)
-    {
-      ProfScope ps(plan, 4, st);
-      rc = launch_sde_update(x, plan->eps, 64, nullptr, c, ZEDO_PRED_EULER_MARUYAMA, 1, nullptr, x, B, D, st);
-    }
-    if (rc) return rc;
-    while (next_dump < n_dump && dump_steps[next_dump] == i) {
-      ZEDO_CUDA_TRY(cudaMemcpyAsync(dump + (size_t)next_dump * B * D, x, (size_t)B * D * sizeof(float),
-                                    cudaMemcpyDeviceToDevice, st));
-      ++next_dump;
-    }
+    prev = subvp_coef(t_sched[i], beta_min, beta_max, n_scales);
   }
+  {
+    // pc_sampler with probability_flow=True, noise_removal=True returns x_mean (sampling.py:524-527)
+    ProfScope ps(plan, 4, st);
+    rc = launch_sde_update(x, plan->eps, 64, nullptr, prev, ZEDO_PRED_EULER_MARUYAMA, 1, nullptr, x, B, D, st);
+  }
+  if (rc) return rc;
+  if (next_dump < n_dump && dump_steps[next_dump] == steps - 1)
+    ZEDO_CUDA_TRY(cudaMemcpyAsync(dump + (size_t)next_dump * B * D, x, (size_t)B * D * sizeof(float),
+                                  cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
@@ -804,6 +812,24 @@ int zedo_eval_multi(const float* pred, const double* gt, int32_t protocol2, int6
     ZEDO_CUDA_TRY(cudaMemcpyAsync(sub, joint_subset, (size_t)n_sub * sizeof(int), cudaMemcpyHostToDevice, st));
   }
   int rc = launch_eval_multi(pred, gt, protocol2, N, S, J, sub, n_sub, err_min, argmin, err_all, aligned, st);
+  if (sub) cudaFreeAsync(sub, st);
+  return rc;
+}
+
+int zedo_pck_counts(const float* pred, const double* gt, const int32_t* select, int64_t N, int32_t S, int32_t J,
+                    const int32_t* joint_subset, int32_t n_sub, uint64_t* counts, void* stream) {
+  if (N == 0) return 0;
+  if (!pred || !gt || !counts) return ZEDO_E_INVALID;
+  if (J < 1 || J > 32 || S < 1 || N < 0) return ZEDO_E_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  int* sub = nullptr;
+  if (joint_subset != nullptr) {
+    if (n_sub < 1 || n_sub > J) return ZEDO_E_SHAPE;
+    ZEDO_CUDA_TRY(cudaMallocAsync((void**)&sub, (size_t)n_sub * sizeof(int), st));
+    ZEDO_CUDA_TRY(cudaMemcpyAsync(sub, joint_subset, (size_t)n_sub * sizeof(int), cudaMemcpyHostToDevice, st));
+  }
+  ZEDO_CUDA_TRY(cudaMemsetAsync(counts, 0, 31 * sizeof(uint64_t), st));
+  int rc = launch_pck_counts(pred, gt, select, N, S, J, sub, n_sub, (unsigned long long*)counts, st);
   if (sub) cudaFreeAsync(sub, st);
   return rc;
 }

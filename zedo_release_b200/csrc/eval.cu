@@ -139,6 +139,47 @@ eval_multi_kernel(const float* __restrict__ pred, const double* __restrict__ gt,
   }
 }
 
+// PCK / AUC of MPI-INF-3DHP (utils.py:814-849, used by mpii3dHP.py:480-481): per-joint error (mm) of the
+// selected hypothesis against 31 thresholds linspace(0, 150, 31); counts[k] += #(error_mm < 5 k).
+__global__ void __launch_bounds__(128)
+pck_counts_kernel(const float* __restrict__ pred, const double* __restrict__ gt, const int* __restrict__ select,
+                  int64_t N, int S, int J, const int* __restrict__ subset, int n_sub,
+                  unsigned long long* __restrict__ counts) {
+  __shared__ unsigned int local[31];
+  if (threadIdx.x < 31) local[threadIdx.x] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n < N && lane < J) {
+    bool counted = true;
+    if (subset != nullptr) {
+      counted = false;
+      for (int i = 0; i < n_sub; ++i) counted |= (subset[i] == lane);
+    }
+    if (counted) {
+      const int s = select != nullptr ? select[n] : 0;
+      const float* pp = pred + ((n * S + s) * J + lane) * 3;
+      const double* gp = gt + (n * J + lane) * 3;
+      const double d0 = (double)pp[0] - gp[0], d1 = (double)pp[1] - gp[1], d2 = (double)pp[2] - gp[2];
+      const double e_mm = sqrt(d0 * d0 + d1 * d1 + d2 * d2) * 1000.0;
+      for (int k = 0; k < 31; ++k)
+        if (e_mm < 5.0 * k) atomicAdd(&local[k], 1u);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 31 && local[threadIdx.x] != 0) atomicAdd(&counts[threadIdx.x], (unsigned long long)local[threadIdx.x]);
+}
+
+int launch_pck_counts(const float* pred, const double* gt, const int* select, int64_t N, int S, int J,
+                      const int* subset_dev, int n_sub, unsigned long long* counts, cudaStream_t st) {
+  if (N == 0) return 0;
+  const int warps = 4;
+  pck_counts_kernel<<<(unsigned)((N + warps - 1) / warps), warps * 32, 0, st>>>(pred, gt, select, N, S, J, subset_dev,
+                                                                             n_sub, counts);
+  ZEDO_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_eval_multi(const float* pred, const double* gt, int protocol2, int64_t N, int S, int J,
                       const int* subset_dev, int n_sub, double* err_min, int* argmin, double* err_all,
                       double* aligned, cudaStream_t st) {

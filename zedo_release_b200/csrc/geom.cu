@@ -14,10 +14,19 @@ namespace zedo {
 
 constexpr int kGeomWarps = 8;
 
+// Euler-Maruyama probability-flow update of one coordinate, float32 op order of sampling.py:185-191 /
+// sde_lib.py:93-100 / utils.py:762-776: score = -eps/std; drift = (-0.5 beta) x - g^2 score; x + drift*dt
+__device__ __forceinline__ float em_pf_update(float xv, float e, float neg_half_beta, float g2, float std, float dt) {
+  const float score = -e / std;
+  const float drift = neg_half_beta * xv - g2 * score;
+  return xv + drift * dt;
+}
+
 __global__ void __launch_bounds__(kGeomWarps * 32)
 grad_field_kernel(const float* __restrict__ uv, const float* x, const float* __restrict__ Kmat,
                   float* conf, float* T, int solve_T, int clamp_inplace, float* g_out, float* x_out,
-                  __half* __restrict__ xa, int64_t B, int J) {
+                  __half* __restrict__ xa, int64_t B, int J, const float* __restrict__ eps_prev, float neg_half_beta,
+                  float gsq, float std, float dt, float* __restrict__ dump) {
   __shared__ float stage[kGeomWarps][kBlockK];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -41,6 +50,19 @@ grad_field_kernel(const float* __restrict__ uv, const float* x, const float* __r
     X0 = xp[0];
     X1 = xp[1];
     X2 = xp[2];
+    if (eps_prev != nullptr) {
+      // fused tail of the previous OIL step: the predictor update with that step's network output
+      const float* ep = eps_prev + pose * 64 + lane * 3;
+      X0 = em_pf_update(X0, ep[0], neg_half_beta, gsq, std, dt);
+      X1 = em_pf_update(X1, ep[1], neg_half_beta, gsq, std, dt);
+      X2 = em_pf_update(X2, ep[2], neg_half_beta, gsq, std, dt);
+      if (dump != nullptr) {
+        float* dp = dump + (pose * J + lane) * 3;
+        dp[0] = X0;
+        dp[1] = X1;
+        dp[2] = X2;
+      }
+    }
     if (conf != nullptr) {
       c = conf[pose * J + lane];
       if (c > 1.f) c = 1.f;          // conf[conf > 1] = 1        (:65)
@@ -180,8 +202,7 @@ __global__ void sde_update_kernel(const float* __restrict__ x, const float* __re
   const float score = -eps[row * ld_eps + e] / std;
   float xm;
   if (predictor == ZEDO_PRED_EULER_MARUYAMA) {
-    const float drift = neg_half_beta * xv - g2 * score;
-    xm = xv + drift * dt;
+    xm = em_pf_update(xv, eps[row * ld_eps + e], neg_half_beta, g2, std, dt);
   } else {
     const float f = neg_half_beta * xv * dt;
     const float rev_f = f - g2 * score;
@@ -198,12 +219,21 @@ __global__ void sde_update_kernel(const float* __restrict__ x, const float* __re
 // ---- host launchers ---------------------------------------------------------------------------------
 
 int launch_grad_field(const float* uv, const float* x, const float* K, float* conf, float* T, int solve_T,
-                      int clamp_inplace, float* g, float* x_out, __half* xa, int64_t B, int J,
-                      cudaStream_t st) {
+                      int clamp_inplace, float* g, float* x_out, __half* xa, int64_t B, int J, cudaStream_t st,
+                      const float* eps_prev, const SdeCoef* prev, float* dump) {
   if (B == 0) return 0;
   const int64_t blocks = (B + kGeomWarps - 1) / kGeomWarps;
+  float nhb = 0.f, g2 = 0.f, sd = 1.f, dt = 0.f;
+  if (eps_prev != nullptr && prev != nullptr) {
+    nhb = -0.5f * prev->beta_t;
+    g2 = prev->diffusion * prev->diffusion;
+    sd = prev->std;
+    dt = prev->dt;
+  } else {
+    eps_prev = nullptr;
+  }
   grad_field_kernel<<<(unsigned)blocks, kGeomWarps * 32, 0, st>>>(uv, x, K, conf, T, solve_T, clamp_inplace, g,
-                                                                  x_out, xa, B, J);
+                                                                  x_out, xa, B, J, eps_prev, nhb, g2, sd, dt, dump);
   ZEDO_LAUNCH_CHECK();
   return 0;
 }

@@ -23,8 +23,10 @@ struct LayerArgs {
 constexpr int EPI_GN_SILU = 0, EPI_LINEAR_ACT = 1, EPI_LINEAR_F32 = 2;
 int launch_layer_tc(const LayerArgs& a, int bn, int nprod, int epi, int num_sms, cudaStream_t st);
 int launch_layer_tc2(const LayerArgs& a, int nprod, int epi, int num_sms, cudaStream_t st);
+// eps_prev/prev/dump: optional fused tail of the previous OIL step (predictor update with that step's eps)
 int launch_grad_field(const float* uv, const float* x, const float* K, float* conf, float* T, int solve_T,
-                      int clamp_inplace, float* g, float* x_out, __half* xa, int64_t B, int J, cudaStream_t st);
+                      int clamp_inplace, float* g, float* x_out, __half* xa, int64_t B, int J, cudaStream_t st,
+                      const float* eps_prev = nullptr, const SdeCoef* prev = nullptr, float* dump = nullptr);
 int launch_pack_x(const float* x, __half* xa, int64_t B, int D, cudaStream_t st);
 int launch_sde_update(const float* x, const float* eps, int ld_eps, const float* z, const SdeCoef& c, int predictor,
                       int probability_flow, float* x_next, float* x_mean, int64_t B, int D, cudaStream_t st);
@@ -44,6 +46,8 @@ int launch_rotopt_forward(const float* q, const float* scale, const float* xk, c
 int launch_rotopt_backward(const float* q, const float* scale, const float* xk, const float* T0, const float* K,
                            float minT, float maxT, const float* d_uv, float* d_q, float* d_scale, int64_t B, int nk,
                            cudaStream_t st);
+int launch_pck_counts(const float* pred, const double* gt, const int* select, int64_t N, int S, int J,
+                      const int* subset_dev, int n_sub, unsigned long long* counts, cudaStream_t st);
 int launch_eval_multi(const float* pred, const double* gt, int protocol2, int64_t N, int S, int J,
                       const int* subset_dev, int n_sub, double* err_min, int* argmin, double* err_all,
                       double* aligned, cudaStream_t st);

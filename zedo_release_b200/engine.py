@@ -232,6 +232,24 @@ def eval_multi(pred: torch.Tensor, gt: torch.Tensor, protocol2: bool = False,
     return out
 
 
+def pck_auc(pred: torch.Tensor, gt: torch.Tensor, select: Optional[torch.Tensor] = None,
+            joint_subset: Optional[Sequence[int]] = None) -> Tuple[float, float]:
+    """(PCK@150mm, AUC) of MPI-INF-3DHP (utils.py:814-849) for the hypothesis ``select[n]`` of every pose
+    (the argmin returned by ``eval_multi``; None = hypothesis 0).  pred [N,S,J,3] f32, gt [N,J,3]."""
+    pred = _f32(pred, "pred")
+    gt = gt.contiguous().double()
+    N, S, J = pred.shape[0], pred.shape[1], pred.shape[2]
+    if select is not None:
+        select = select.contiguous().to(torch.int32)
+    counts = torch.zeros((31,), dtype=torch.int64, device=pred.device)
+    sub = nat.i32_array(joint_subset) if joint_subset is not None else None
+    nat.check(nat.lib.zedo_pck_counts(_ptr(pred), _ptr(gt), _ptr(select), N, S, J, sub,
+                                      len(sub) if sub is not None else 0, _ptr(counts), _stream()), "zedo_pck_counts")
+    total = N * (len(sub) if sub is not None else J)
+    pcks = 100.0 * counts.cpu().numpy().astype(np.float64) / max(total, 1)
+    return float(pcks[30]), float(pcks.mean())
+
+
 def aggregate_errors(err_min, actions=None) -> float:
     """H36M: mean over actions 2..16 of the per-action means (h36m.py:424-433); otherwise the
     plain mean (pw3d.py:338).  Host-side numpy over the [N] float64 result vector."""
