@@ -105,6 +105,8 @@ struct zedo_plan {
   float* post_bias = nullptr;  // [64]
   std::vector<PackedWeight> packed;
   std::vector<PackedWeight> packed_pair;  // 1024 -> 1024 layers again, 128-row tiles for the CTA-pair kernel
+  std::vector<PackedWeight> packed64;     // hidden-width layers again, 64-row tiles: small-batch latency mode
+  int small_batch_tiles = 18;             // use the 64-wide tiles when the batch has at most this many 128-row tiles
   std::vector<GemmOp> program;
   bool use_pairs = true;
 
@@ -323,7 +325,12 @@ int net_forward(zedo_plan* p, const float* x, const float* tbl, int64_t B, int m
     {
       ProfScope ps(p, op.epi == EPI_LINEAR_F32 ? 2 : (a.num_kb == 1 ? 0 : 1), st);
       const PackedWeight& wp = p->packed_pair[op.weight];
-      if (p->use_pairs && wp.dev != nullptr && op.epi != EPI_LINEAR_F32) {
+      const PackedWeight& w64 = p->packed64[op.weight];
+      if (m_tiles <= p->small_batch_tiles && w64.dev != nullptr && op.epi != EPI_LINEAR_F32) {
+        a.W = w64.dev;  // few poses: 64-channel tiles keep all SMs busy and cut the per-tile MMA chain by 4
+        a.n_tiles = w64.n_pad / 64;
+        rc = launch_layer_tc(a, 64, nprod, op.epi, p->num_sms, st);
+      } else if (p->use_pairs && wp.dev != nullptr && op.epi != EPI_LINEAR_F32) {
         a.W = wp.dev;                        // CTA-pair kernel: 256 poses x 256 channels per cluster
         a.m_tiles = (m_tiles + 1) & ~1;      // activation buffers are padded to 256 rows
         rc = launch_layer_tc2(a, nprod, op.epi, p->num_sms, st);
@@ -397,6 +404,7 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
   p->cap = max_batch;
   p->m_pad = round_up(max_batch, 2 * kActTileRows);  // CTA pairs work on 256 rows
   p->use_pairs = !(getenv("ZEDO_TC2") && atoi(getenv("ZEDO_TC2")) == 0);
+  if (getenv("ZEDO_SMALL_TILES")) p->small_batch_tiles = atoi(getenv("ZEDO_SMALL_TILES"));
   int rc = 0;
 #define PLAN_TRY(expr)         \
   do {                         \
@@ -433,10 +441,15 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
   auto add_weight = [&](const std::string& name, int N, int K, int bn) -> int {
     const std::vector<float>* w = tm.get(name + ".weight", (size_t)N * K);
     if (!w) return ZEDO_E_MISSING;
-    PackedWeight pw, pw2;
+    PackedWeight pw, pw2, pw64;
     int r = pack_weight(w->data(), N, K, bn, &pw);
     if (r) return r > 0 ? -1000 - r : r;
     p->owned.push_back(pw.dev);
+    if (N == H) {
+      if ((r = pack_weight(w->data(), N, K, 64, &pw64))) return r > 0 ? -1000 - r : r;
+      p->owned.push_back(pw64.dev);
+    }
+    p->packed64.push_back(pw64);
     if (K == H && N == H) {
       if ((r = pack_weight(w->data(), N, K, 128, &pw2))) return r > 0 ? -1000 - r : r;
       p->owned.push_back(pw2.dev);

@@ -187,12 +187,9 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) layer_tc_kernel(const Layer
 template <int BN, int NPROD, int EPI, int EW>
 static int launch_ew(const LayerArgs& a, int num_sms, cudaStream_t st) {
   using Cfg = TileCfg<BN, NPROD>;
-  static bool configured = false;
   auto kern = layer_tc_kernel<BN, NPROD, EPI, EW>;
-  if (!configured) {
-    ZEDO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
-  }
+  // per call, not cached: the attribute is per device and a process may own plans on several devices
+  ZEDO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   const int tiles = a.m_tiles * a.n_tiles;
   if (tiles == 0) return 0;
   const int grid = tiles < num_sms ? tiles : num_sms;
@@ -227,6 +224,9 @@ int launch_layer_tc(const LayerArgs& a_in, int bn, int nprod, int epi, int num_s
   if (bn == 256 && epi == EPI_GN_SILU) return launch_nprod<256, EPI_GN_SILU>(a, nprod, num_sms, st);
   if (bn == 256 && epi == EPI_LINEAR_ACT) return launch_nprod<256, EPI_LINEAR_ACT>(a, nprod, num_sms, st);
   if (bn == 64 && epi == EPI_LINEAR_F32) return launch_nprod<64, EPI_LINEAR_F32>(a, nprod, num_sms, st);
+  // narrow tiles for small batches: 4x more CTAs, each with a 4x shorter MMA chain (latency mode)
+  if (bn == 64 && epi == EPI_GN_SILU) return launch_nprod<64, EPI_GN_SILU>(a, nprod, num_sms, st);
+  if (bn == 64 && epi == EPI_LINEAR_ACT) return launch_nprod<64, EPI_LINEAR_ACT>(a, nprod, num_sms, st);
   return ZEDO_E_INVALID;
 }
 

@@ -226,12 +226,8 @@ layer_tc2_kernel(const LayerArgs args) {
 template <int NPROD, int EPI, int EW>
 static int launch_pair_ew(const LayerArgs& a, int num_sms, cudaStream_t st) {
   using Cfg = PairCfg<NPROD>;
-  static bool configured = false;
   auto kern = layer_tc2_kernel<NPROD, EPI, EW>;
-  if (!configured) {
-    ZEDO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
-  }
+  ZEDO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   if (a.m_tiles % 2 != 0) return ZEDO_E_SHAPE;
   const int pairs = (a.m_tiles / 2) * a.n_tiles;
   if (pairs == 0) return 0;
