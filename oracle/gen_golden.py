@@ -381,6 +381,45 @@ def main():
     out["oil"] = dict(R=R_ref, T=T_ref, x0=x0, T_final=Tt.numpy(),
                       steps=np.array(sorted(dumps_ref)), poses=np.stack([dumps_ref[i] for i in sorted(dumps_ref)]))
 
+    # ---- 7b. the same loop with a damped network: poses stay at realistic scale (MPJPE ~ 0.1 m) ------------
+    # Is the cumulative drift a property of the random-init network?  No: with post_dense scaled by 0.05 (network
+    # push 20x smaller) two float32 implementations still end ~1e-3 apart.  The source is the per-step least-squares
+    # translation (cond ~ 1e3 along the depth axis): the reference's float32 solve is 4.5e-6 off the exact solution
+    # (2e-5 m), a random walk over 800 phase-2 steps; x is never re-centred, so depth noise lands in MPJPE directly.
+    # Per-pose MPJPE of the reference is therefore only reproducible to ~1 mm across BLAS/LAPACK stacks; the
+    # aggregate (mean over poses) is much tighter.
+    print("OIL loop, damped network (1000 steps, B=16)")
+    Ws = dict(W)
+    Ws["post_dense.weight"] = (W["post_dense.weight"] * np.float32(0.05)).astype(np.float32)
+    Ws["post_dense.bias"] = (W["post_dense.bias"] * np.float32(0.05)).astype(np.float32)
+    model_s = load_into(torch, R.ScoreModelFC_Adv(cfg, n_joints=17, joint_dim=3, hidden_dim=1024, embed_dim=512,
+                                                  cond_dim=3), Ws)
+    conf_t = torch.tensor(uvc[:, :, 2].copy())
+    with torch.no_grad():
+        dx = torch.tensor(R_ref).bmm(torch.tensor(x0).permute(0, 2, 1)).permute(0, 2, 1).contiguous()
+        Tt = torch.tensor(T_ref)
+        for i in range(n_steps):
+            if i < n_steps // 5:
+                jg = R.szo.gradient_field_gen(uv_t, dx, Kt, t=Tt, conf=conf_t, returnT=False)
+            else:
+                jg, Tt = R.szo.gradient_field_gen(uv_t, dx, Kt, conf=conf_t, returnT=True)
+            dx += jg
+            _, results = sampling_fn(model_s, condition=uv_t * 0, gradient=jg, denoise_x=dx, t=ts[i], t_step=i,
+                                     args=None)
+            dx = torch.tensor(results)
+    xs, Ts, _ = zo.oil_loop(Ws, x_rot, T_ref, uvc[:, :, :2], Kc, uvc[:, :, 2].copy())
+    ck.check("damped OIL final pose (cumulative)", xs, results, 3e-3)
+    mp_ref = np.array([zo.mpjpe(results[n], gt16[n]) for n in range(B)])
+    mp_or = np.array([zo.mpjpe(xs[n], gt16[n]) for n in range(B)])
+    print(f"      (info) damped loop MPJPE level {mp_ref.mean():.4f} m")
+    print(f"      (info) per-pose |dMPJPE| mean {np.abs(mp_ref - mp_or).mean() * 1e3:.3f} mm, max "
+          f"{np.abs(mp_ref - mp_or).max() * 1e3:.3f} mm; aggregate {abs(mp_ref.mean() - mp_or.mean()) * 1e3:.4f} mm")
+    ck.bound("damped OIL per-pose |dMPJPE| max in metres (float32 noise floor, tol 3 mm)",
+             np.abs(mp_ref - mp_or).max(), 3e-3)
+    ck.bound("damped OIL aggregate |dMPJPE| in metres (tol 0.1 mm per metre of MPJPE)",
+             abs(mp_ref.mean() - mp_or.mean()), 1e-4 * max(1.0, mp_ref.mean()))
+    out["oil_small"] = dict(x_final=results, T_final=Tt.numpy(), post_scale=np.float32(0.05), mpjpe=mp_ref)
+
     # ---- 8. Procrustes and eval_multi ---------------------------------------------------------------
     print("procrustes / eval_multi")
     rng = np.random.default_rng(11)

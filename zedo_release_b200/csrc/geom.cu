@@ -14,6 +14,12 @@ namespace zedo {
 
 constexpr int kGeomWarps = 8;
 
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 // Euler-Maruyama probability-flow update of one coordinate, float32 op order of sampling.py:185-191 /
 // sde_lib.py:93-100 / utils.py:762-776: score = -eps/std; drift = (-0.5 beta) x - g^2 score; x + drift*dt
 __device__ __forceinline__ float em_pf_update(float xv, float e, float neg_half_beta, float g2, float std, float dt) {
@@ -82,19 +88,23 @@ grad_field_kernel(const float* __restrict__ uv, const float* x, const float* __r
     const float w = active ? c * c : 0.f;  // row weight conf*conf on A and on b  (:85-88)
     const float bx = (X0 - X2 * rx) * w, by = (X1 - X2 * ry) * w;
     const float ax = rx * w, ay = ry * w, am = -w;
-    float S = warp_sum(am * am);
-    float Sxz = warp_sum(am * ax);
-    float Syz = warp_sum(am * ay);
-    float Szz = warp_sum(ax * ax + ay * ay);
-    float b0 = warp_sum(am * bx);
-    float b1 = warp_sum(am * by);
-    float b2 = warp_sum(ax * bx + ay * by);
-    float M[9] = {S, 0.f, Sxz, 0.f, S, Syz, Sxz, Syz, Szz};
-    float Mi[9];
-    inv3x3(M, Mi);
-    T0 = Mi[0] * b0 + Mi[1] * b1 + Mi[2] * b2;
-    T1 = Mi[3] * b0 + Mi[4] * b1 + Mi[5] * b2;
-    T2 = Mi[6] * b0 + Mi[7] * b1 + Mi[8] * b2;
+    // The normal equations are ill-conditioned along the depth axis (cond ~ 1e3): the float32 products are
+    // formed exactly as the reference forms them (A and b rows already multiplied by w), but the seven sums
+    // and the 3x3 solve run in float64, so this kernel returns the exact solution of the reference's system
+    // and differs from the reference only by the reference's own float32 rounding.
+    const double S = warp_sum_f64((double)(am * am));
+    const double Sxz = warp_sum_f64((double)(am * ax));
+    const double Syz = warp_sum_f64((double)(am * ay));
+    const double Szz = warp_sum_f64((double)(ax * ax) + (double)(ay * ay));
+    const double b0 = warp_sum_f64((double)(am * bx));
+    const double b1 = warp_sum_f64((double)(am * by));
+    const double b2 = warp_sum_f64((double)(ax * bx) + (double)(ay * by));
+    // M = [[S,0,Sxz],[0,S,Syz],[Sxz,Syz,Szz]]: eliminate the two S rows (Schur complement on the depth axis)
+    const double den = Szz - (Sxz * Sxz + Syz * Syz) / S;
+    const double tz = (b2 - (Sxz * b0 + Syz * b1) / S) / den;
+    T0 = (float)((b0 - Sxz * tz) / S);
+    T1 = (float)((b1 - Syz * tz) / S);
+    T2 = (float)tz;
     if (T2 < 0.f) {  // T[T_z < 0] *= -1  (:93)
       T0 = -T0;
       T1 = -T1;
