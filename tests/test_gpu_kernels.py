@@ -484,3 +484,44 @@ def test_full_size_batch_properties(zr):
     p.oil_loop(xb, Tb, uv[sel].contiguous(), K[sel].contiguous(), conf[sel].clone(), ts, phase_switch=1)
     assert torch.equal(xa[sel], xb) and torch.equal(Ta[sel], Tb)
     p.close()
+
+
+@pytest.mark.parametrize("J,cfg_name", [(12, "SYRIP_ZEDO_CFG"), (17, "PW3D_ZEDO_CFG")])
+def test_oil_loop_other_configs_vs_oracle(zr, J, cfg_name):
+    """SyRIP-format J = 12 (infant phase switch late in the loop, no confidences) and the 3DPW config: a 40-step
+    loop across the phase switch against the oracle, from the same (R, T)."""
+    B = 200
+    cfg = getattr(zo, cfg_name)
+    W = zo.make_weights(seed=4, n_joints=J)
+    ds = zo.make_synthetic_dataset(B, n_joints=J, seed=J + 1, n_clusters=1)
+    uv, K = ds["db_2d"][:, :, :2], ds["camera_param"]
+    conf = None if J == 12 else ds["db_2d"][:, :, 2]
+    x0 = zo.init_hypothesis(ds["clusters"], 0, B)
+    R, T, x_rot, _ = zr.ipo_fit(dev(x0), dev(uv), dev(K), cfg["IPO_keylist"], cfg["RotAxes"], cfg["IPO_T"],
+                                cfg["IPO_minScaleT"], cfg["IPO_maxScaleT"], iters=40)
+    ts = zo.oil_time_grid()[930:970]
+    p = zr.ScorePlan(W, n_joints=J, max_batch=B, device=0)
+    xg, Tg = x_rot.clone(), T.clone()
+    p.oil_loop(xg, Tg, dev(uv), dev(K), None if conf is None else dev(conf), ts, phase_switch=20)
+    p.close()
+    xo, To, _ = zo.oil_loop_schedule(W, x_rot.cpu().numpy(), T.cpu().numpy().reshape(B, 1, 3), uv, K,
+                                     None if conf is None else conf.copy(), ts, 20)
+    assert rel_err(xg.cpu().numpy(), xo) < 2e-4
+    assert rel_err(Tg.cpu().numpy(), To.reshape(B, 3)) < 2e-4
+
+
+def test_multi_hypothesis_selection_matches_oracle(zr, plan17):
+    """Cluster-initialised hypotheses end to end: the argmin over hypotheses computed on the GPU results is
+    bit-exact against the oracle's eval_multi on the same results, both protocols."""
+    B, S = 128, 6
+    ds = zo.make_synthetic_dataset(B, seed=77, n_clusters=S)
+    res = zr.run_pose_optimisation(plan17, dev(ds["db_2d"]), dev(ds["camera_param"]), dev(ds["clusters"]),
+                                   dict(zo.H36M_ZEDO_CFG), hypo=S, steps=30)
+    gt = ds["db_3d"].astype(np.float64)
+    for p2 in (False, True):
+        e, idx = zr.eval_multi(res, dev(gt, torch.float64), protocol2=p2)
+        agg_o, res_o, idx_o = zo.eval_multi(res.cpu().numpy(), gt, protocol2=p2, actions=ds["actions"])
+        assert np.array_equal(idx.cpu().numpy(), idx_o)
+        assert np.abs(e.cpu().numpy() - res_o).max() < (2e-7 if p2 else 1e-12)
+        assert abs(zr.aggregate_errors(e, ds["actions"]) - agg_o) < 2e-7
+    assert len(set(idx.cpu().numpy().tolist())) > 1  # different poses pick different hypotheses
