@@ -14,6 +14,11 @@
 
 namespace zedo {
 
+bool pdl_enabled() {
+  static const bool on = !(getenv("ZEDO_PDL") && atoi(getenv("ZEDO_PDL")) == 0);
+  return on;
+}
+
 static std::atomic<int64_t> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 

@@ -25,6 +25,33 @@ void count_launch(int n = 1);
     if (_e != cudaSuccess) return (int)_e;         \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------
+// Kernels of the OIL loop are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next
+// kernel may be scheduled while the previous one drains, runs its prologue (barrier init, TMEM allocation)
+// and then blocks in griddep_wait() until the previous grid has completed and flushed.  Every kernel
+// launched that way calls griddep_wait() before it touches global memory written by a predecessor.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool pdl_enabled();  // env ZEDO_PDL (default on)
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // ---- blocked, core-matrix-interleaved fp16 operand layout ------------------------------------------
 // A [rows, cols] fp16 operand (cols padded to a multiple of 64) is stored as tiles of
 // TILE_ROWS x 64 halves; tile (rt, kb) has a "hi" image followed by a "lo" image, each

@@ -37,6 +37,7 @@ grad_field_kernel(const float* __restrict__ uv, const float* x, const float* __r
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int64_t pose = (int64_t)blockIdx.x * kGeomWarps + wib;
+  griddep_wait();  // PDL: x / eps come from the previous kernels (multi-wave grid: dependents launch at exit)
   if (pose >= B) return;
   const bool active = lane < J;
 
@@ -176,6 +177,7 @@ __global__ void pack_x_kernel(const float* __restrict__ x, __half* __restrict__ 
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t row = t >> 3;
   const int chunk = (int)(t & 7);
+  griddep_wait();
   if (row >= B) return;
   uint32_t hi[4], lo[4];
 #pragma unroll
@@ -205,6 +207,7 @@ __global__ void sde_update_kernel(const float* __restrict__ x, const float* __re
                                   float dt, float noise_scale, int predictor, float* x_next, float* x_mean,
                                   int64_t B, int D) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  griddep_wait();
   if (idx >= B * D) return;
   const int64_t row = idx / D;
   const int e = (int)(idx - row * D);
@@ -242,8 +245,8 @@ int launch_grad_field(const float* uv, const float* x, const float* K, float* co
   } else {
     eps_prev = nullptr;
   }
-  grad_field_kernel<<<(unsigned)blocks, kGeomWarps * 32, 0, st>>>(uv, x, K, conf, T, solve_T, clamp_inplace, g,
-                                                                  x_out, xa, B, J, eps_prev, nhb, g2, sd, dt, dump);
+  ZEDO_CUDA_TRY(launch_pdl(grad_field_kernel, dim3((unsigned)blocks), dim3(kGeomWarps * 32), 0, st, uv, x, K, conf, T,
+                           solve_T, clamp_inplace, g, x_out, xa, B, J, eps_prev, nhb, g2, sd, dt, dump));
   ZEDO_LAUNCH_CHECK();
   return 0;
 }
@@ -251,7 +254,7 @@ int launch_grad_field(const float* uv, const float* x, const float* K, float* co
 int launch_pack_x(const float* x, __half* xa, int64_t B, int D, cudaStream_t st) {
   if (B == 0) return 0;
   const int64_t threads = B * 8;
-  pack_x_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, xa, B, D);
+  ZEDO_CUDA_TRY(launch_pdl(pack_x_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, x, xa, B, D));
   ZEDO_LAUNCH_CHECK();
   return 0;
 }
@@ -274,8 +277,8 @@ int launch_sde_update(const float* x, const float* eps, int ld_eps, const float*
     noise_scale = probability_flow ? 0.f : G;
   }
   const int64_t n = B * D;
-  sde_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, eps, ld_eps, z, -0.5f * c.beta_t, g2, c.std,
-                                                                 dt, noise_scale, predictor, x_next, x_mean, B, D);
+  ZEDO_CUDA_TRY(launch_pdl(sde_update_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x, eps, ld_eps, z,
+                           -0.5f * c.beta_t, g2, c.std, dt, noise_scale, predictor, x_next, x_mean, B, D));
   ZEDO_LAUNCH_CHECK();
   return 0;
 }

@@ -72,6 +72,9 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) layer_tc_kernel(const Layer
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above overlapped with the tail of the previous kernel; from here on its output is read
+  griddep_wait();
+  griddep_launch_dependents();  // persistent single-wave grid: the next kernel may queue up behind our CTAs
 
   const int num_tiles = args.m_tiles * args.n_tiles;
   const int num_kb = args.num_kb;
@@ -193,7 +196,7 @@ static int launch_ew(const LayerArgs& a, int num_sms, cudaStream_t st) {
   const int tiles = a.m_tiles * a.n_tiles;
   if (tiles == 0) return 0;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, tc_threads(EW), Cfg::kSmemBytes, st>>>(a);
+  ZEDO_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(tc_threads(EW)), Cfg::kSmemBytes, st, a));
   ZEDO_LAUNCH_CHECK();
   return 0;
 }

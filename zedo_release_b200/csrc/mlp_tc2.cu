@@ -105,6 +105,8 @@ layer_tc2_kernel(const LayerArgs args) {
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();                // PDL: the prologue above overlapped with the previous kernel's tail
+  griddep_launch_dependents();
 
   const int num_kb = args.num_kb;
   const int num_pairs = (args.m_tiles / 2) * args.n_tiles;  // m_tiles is even (plan pads to 256 rows)
@@ -233,7 +235,7 @@ static int launch_pair_ew(const LayerArgs& a, int num_sms, cudaStream_t st) {
   if (pairs == 0) return 0;
   const int max_pairs = num_sms / 2;
   const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
-  kern<<<grid, tc_threads(EW), Cfg::kSmemBytes, st>>>(a);
+  ZEDO_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(tc_threads(EW)), Cfg::kSmemBytes, st, a));
   ZEDO_LAUNCH_CHECK();
   return 0;
 }
