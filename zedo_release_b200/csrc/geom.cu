@@ -101,10 +101,11 @@ grad_field_kernel(const float* __restrict__ uv, const float* x, const float* __r
     const double b1 = warp_sum_f64((double)(am * by));
     const double b2 = warp_sum_f64((double)(ax * bx) + (double)(ay * by));
     // M = [[S,0,Sxz],[0,S,Syz],[Sxz,Syz,Szz]]: eliminate the two S rows (Schur complement on the depth axis)
-    const double den = Szz - (Sxz * Sxz + Syz * Syz) / S;
-    const double tz = (b2 - (Sxz * b0 + Syz * b1) / S) / den;
-    T0 = (float)((b0 - Sxz * tz) / S);
-    T1 = (float)((b1 - Syz * tz) / S);
+    const double iS = 1.0 / S;
+    const double den = Szz - (Sxz * Sxz + Syz * Syz) * iS;
+    const double tz = (b2 - (Sxz * b0 + Syz * b1) * iS) / den;
+    T0 = (float)((b0 - Sxz * tz) * iS);
+    T1 = (float)((b1 - Syz * tz) * iS);
     T2 = (float)tz;
     if (T2 < 0.f) {  // T[T_z < 0] *= -1  (:93)
       T0 = -T0;
