@@ -63,6 +63,19 @@ def test_mirror_registries_and_error_conventions(zr):
         sampling.AncestralSamplingPredictor(sde, lambda *a: None)
     with pytest.raises(NotImplementedError):
         mutils.get_score_fn(object(), None)
+    # Langevin corrector + sub-VP SDE: the reference reads sde.alphas, which only VPSDE defines -> AttributeError
+    with pytest.raises(AttributeError):
+        sampling.LangevinCorrector(sde, lambda *a: None, 0.16, 1).update_fn(torch.zeros(2, 17, 3), torch.ones(2) * 0.05,
+                                                                              None, None)
+    vp = sde_lib.VPSDE(beta_min=0.1, beta_max=20., N=1000, T=1)
+    xs, xm = sampling.LangevinCorrector(vp, lambda x, t, c, m: -x, 0.16, 2).update_fn(
+        torch.ones(3, 17, 3), torch.ones(3) * 0.5, None, None)
+    assert xs.shape == (3, 17, 3) and torch.isfinite(xs).all() and torch.isfinite(xm).all()
+    rs = sde.reverse(lambda x, t, c, m: x * 0 + 2.0, probability_flow=True)  # module-level reverse-time object
+    drift, diff = rs.sde(torch.ones(2, 17, 3), torch.tensor([0.1, 0.05]), None, None)
+    assert rs.N == 1000 and rs.T == 0.1 and float(diff.sum()) == 0.0 and rs.beta_1 == 20.0
+    b, g = zo.subvp_sde_scalars(np.float32([0.1, 0.05]))
+    assert np.allclose(drift[:, 0, 0].numpy(), -0.5 * b - g ** 2 * 2.0, rtol=1e-5)
     # sub-VP schedule of the mirror == oracle scalars
     t = torch.tensor([0.1, 0.05, 0.01])
     _, g = sde.sde(torch.zeros(3, 1, 1), t)
@@ -110,7 +123,10 @@ def _gloo_worker(rank, world, port, n, out_dir):
     full = torch.arange(n * 6, dtype=torch.float32).reshape(n, 2, 3)
     got = parallel.gather_rows(full[lo:hi].clone(), n)
     idx = parallel.gather_rows(torch.arange(lo, hi, dtype=torch.int32), n)
-    ok = torch.equal(got, full) and torch.equal(idx, torch.arange(n, dtype=torch.int32))
+    vals = torch.arange(n, dtype=torch.float32) ** 2
+    gm = parallel.global_batch_mean(vals[lo:hi])  # Langevin's batch-mean norms over uneven shards
+    ok = (torch.equal(got, full) and torch.equal(idx, torch.arange(n, dtype=torch.int32))
+          and abs(float(gm) - float(vals.double().mean())) < 1e-4 * float(vals.mean()))
     open(os.path.join(out_dir, f"rank{rank}.txt"), "w").write("ok" if ok else "bad")
     dist.barrier()
     dist.destroy_process_group()

@@ -14,6 +14,7 @@ import functools
 import numpy as np
 import torch
 
+from zedo_release_b200.parallel import global_batch_mean
 from . import sde_lib
 from . import utils as mutils
 from .utils import from_flattened_numpy, to_flattened_numpy, get_score_fn  # noqa: F401
@@ -177,8 +178,9 @@ class LangevinCorrector(Corrector):
         for _ in range(self.n_steps):
             grad = self.score_fn(x, t, condition, mask)
             noise = torch.randn_like(x)
-            grad_norm = torch.norm(grad.reshape(grad.shape[0], -1), dim=-1).mean()
-            noise_norm = torch.norm(noise.reshape(noise.shape[0], -1), dim=-1).mean()
+            # batch means: taken over ALL ranks when the poses are sharded (one 2-float all_reduce each)
+            grad_norm = global_batch_mean(torch.norm(grad.reshape(grad.shape[0], -1), dim=-1))
+            noise_norm = global_batch_mean(torch.norm(noise.reshape(noise.shape[0], -1), dim=-1))
             step_size = (self.snr * noise_norm / grad_norm) ** 2 * 2 * alpha
             x_mean = x + step_size[:, None, None] * grad
             x = x_mean + torch.sqrt(step_size * 2)[:, None, None] * noise

@@ -55,6 +55,17 @@ def gather_rows(local: torch.Tensor, n_total: int) -> torch.Tensor:
     return torch.cat([out[r, : sizes[r]] for r in range(world)], dim=0)
 
 
+def global_batch_mean(per_pose: torch.Tensor) -> torch.Tensor:
+    """Mean over the GLOBAL batch of a per-pose quantity held as local shards (one all_reduce of a (sum, count)
+    pair).  The Langevin corrector's step size uses batch means of the gradient / noise norms (reference
+    sampling.py:281-283), so a sharded run has to take them over all ranks to match the single-process value."""
+    acc = torch.stack([per_pose.double().sum(), torch.tensor(float(per_pose.numel()), dtype=torch.float64,
+                                                             device=per_pose.device)])
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+    return (acc[0] / acc[1]).to(per_pose.dtype)
+
+
 def run_sharded(plan_factory, db_2d, K, clusters, cfg, hypo=1, mode="split3", gt=None, protocol2=False,
                 actions=None):
     """The whole job on this rank's shard: slice the (host) arrays by ``shard_range``, run IPO + OIL
