@@ -1,18 +1,25 @@
-// K3 / K2: per-step reprojection fit (one warp per pose) and the fused SDE predictor update.
+// K3 / K2: per-step reprojection fit and the fused SDE predictor update.
 //
-// grad_field_kernel restates gradient_field_gen (reference simple_zeroshot_opt.py:46-125):
+// Both geometry kernels restate gradient_field_gen (reference simple_zeroshot_opt.py:46-125):
 //   rays r_j = K^-1 [u_j, v_j, 1], r_j /= r_j.z                                     (:61-71)
 //   optional least-squares translation, rows weighted conf^2, sign flip on T_z < 0   (:73-93)
 //   r^_j = r_j/|r_j|; p_j = X_j + T; g_j = (p_j . r^_j) r^_j - p_j                   (:33-36,99,109)
-// Lane j of the warp owns joint j (J <= 32); the seven normal-equation sums are xor-shuffle
-// reductions, so every lane holds the same T.  The kernel is HBM-bound: per pose it moves
-// x (r/w), uv, conf, K, T = 672 bytes at J = 17 and (optionally) emits the first GEMM's
-// fp16 hi/lo operand in the blocked interleaved layout (common.cuh).
+// Per pose they move x (r/w), uv, conf, K, T = 672 bytes at J = 17 and (optionally) emit the first
+// GEMM's fp16 hi/lo operand in the blocked interleaved layout (common.cuh).
+//   * grad_field_kernel: one warp per pose, lane j owns joint j (J <= 32), xor-shuffle reductions --
+//     lowest latency, used for small batches (it issues ~620 warp instructions per pose).
+//   * grad_field_block_kernel: 128 poses per CTA, inputs staged in shared memory by coalesced loads,
+//     one thread per pose for the serial part (~4x fewer instructions per pose) -- used when the
+//     batch fills the GPU, where the warp kernel is issue-bound rather than HBM-bound.
+#include <cstdlib>
+#include <cstring>
+
 #include "kernels.cuh"
 
 namespace zedo {
 
 constexpr int kGeomWarps = 8;
+constexpr int64_t kGeomBlockMinPoses = 32768;  // >= 256 CTAs of 128 poses
 
 __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
@@ -173,6 +180,210 @@ grad_field_kernel(const float* __restrict__ uv, const float* x, const float* __r
   }
 }
 
+// ---- 128 poses per CTA, four threads per pose ----------------------------------------------------------
+constexpr int kGeomPoses = 128;
+constexpr int kGeomTpp = 4;  // threads per pose in the per-pose phase (joints j = q, q + 4, ...)
+constexpr int kGeomThreads = kGeomPoses * kGeomTpp;
+
+// elements i = tid, tid + 512, ... of an [n, len] row-major block: f(i, row, col) without a division per element
+template <class F>
+__device__ __forceinline__ void for_block_elems(int n, int len, F f) {
+  int row = (int)threadIdx.x / len, col = (int)threadIdx.x - row * len;
+  const int drow = kGeomThreads / len, dcol = kGeomThreads - drow * len;
+  for (int i = threadIdx.x; i < n * len; i += kGeomThreads) {
+    f(i, row, col);
+    row += drow;
+    col += dcol;
+    if (col >= len) {
+      col -= len;
+      ++row;
+    }
+  }
+}
+
+__host__ __device__ inline int geom_block_smem_floats(int J) {
+  const int Jp = J | 1, Dp = (3 * J) | 1;  // odd strides keep the per-pose reads spread over the banks
+  return kGeomPoses * (2 * Jp + Dp + Jp + 9 + 3);
+}
+
+__device__ __forceinline__ double quad_sum_f64(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
+__global__ void __launch_bounds__(kGeomThreads)
+grad_field_block_kernel(const float* __restrict__ uv, const float* x, const float* __restrict__ Kmat, float* conf,
+                        float* T, int solve_T, int clamp_inplace, float* g_out, float* x_out,
+                        __half* __restrict__ xa, int64_t B, int J, const float* __restrict__ eps_prev,
+                        float neg_half_beta, float gsq, float std, float dt, float* __restrict__ dump) {
+  extern __shared__ __align__(16) float geom_smem[];
+  const int D = 3 * J, Jp = J | 1, Dp = D | 1;
+  float2* us = reinterpret_cast<float2*>(geom_smem);  // [P][Jp] (u, v)
+  float* xs = geom_smem + kGeomPoses * 2 * Jp;         // [P][Dp] pose (updated in place)
+  float* cs = xs + kGeomPoses * Dp;                    // [P][Jp] clamped confidence
+  float* ks = cs + kGeomPoses * Jp;                    // [P][9]
+  float* ts = ks + kGeomPoses * 9;                     // [P][3]
+  const int64_t p0 = (int64_t)blockIdx.x * kGeomPoses;
+  const int n = (int)((B - p0) < kGeomPoses ? (B - p0) : kGeomPoses);
+  const int tid = threadIdx.x;
+
+  griddep_wait();  // PDL: x / eps / T come from the previous kernels
+  const float2* uv2 = reinterpret_cast<const float2*>(uv) + p0 * J;
+  for_block_elems(n, J, [&](int i, int r, int c) { us[r * Jp + c] = uv2[i]; });
+  for (int i = tid; i < n * 9; i += kGeomThreads) ks[i] = Kmat[p0 * 9 + i];
+  if (conf != nullptr) {
+    float* cg = conf + p0 * J;
+    for_block_elems(n, J, [&](int i, int r, int c) {
+      float cv = cg[i];
+      if (cv > 1.f) cv = 1.f;        // conf[conf > 1] = 1        (:65)
+      if (cv < 1e-4f) cv = 1e-4f;    // conf[conf < 1e-4] = 1e-4  (:66)
+      if (clamp_inplace) cg[i] = cv;
+      cs[r * Jp + c] = cv;
+    });
+  }
+  {
+    const float* xg = x + p0 * D;
+    float* dg = dump != nullptr ? dump + p0 * D : nullptr;
+    const float* eg = eps_prev != nullptr ? eps_prev + p0 * 64 : nullptr;
+    for_block_elems(n, D, [&](int i, int r, int c) {
+      float xv = xg[i];
+      if (eg != nullptr) {
+        // fused tail of the previous OIL step: the predictor update with that step's network output
+        xv = em_pf_update(xv, eg[r * 64 + c], neg_half_beta, gsq, std, dt);
+        if (dg != nullptr) dg[i] = xv;
+      }
+      xs[r * Dp + c] = xv;
+    });
+  }
+  if (!solve_T)
+    for (int i = tid; i < n * 3; i += kGeomThreads) ts[i] = T[p0 * 3 + i];
+  __syncthreads();
+
+  if (((tid & ~31) >> 2) < n) {
+    // per-pose phase (warps with a live pose): thread (pose, q) owns joints q, q + 4, ...; the idle quads of a
+    // ragged last warp recompute pose n - 1 (the warp stays converged for the shuffles) and discard the result
+    const int pl = tid >> 2, q = tid & 3;
+    const bool live = pl < n;
+    const int pp = live ? pl : n - 1;
+    float Ki[9];
+    inv3x3(ks + pp * 9, Ki);
+    float* xp = xs + pp * Dp;
+    const float2* up = us + pp * Jp;
+    float T0, T1, T2;
+    if (solve_T) {
+      // same float32 products as the reference, float64 sums and solve (see grad_field_kernel)
+      double S = 0, Sxz = 0, Syz = 0, Szz = 0, b0 = 0, b1 = 0, b2 = 0;
+      for (int j = q; j < J; j += kGeomTpp) {
+        const float2 p2 = up[j];
+        float rx = Ki[0] * p2.x + Ki[1] * p2.y + Ki[2];
+        float ry = Ki[3] * p2.x + Ki[4] * p2.y + Ki[5];
+        const float rz = Ki[6] * p2.x + Ki[7] * p2.y + Ki[8];
+        rx = rx / rz;
+        ry = ry / rz;
+        const float c = conf != nullptr ? cs[pp * Jp + j] : 1.f;
+        const float w = c * c;
+        const float X0 = xp[3 * j], X1 = xp[3 * j + 1], X2 = xp[3 * j + 2];
+        const float bx = (X0 - X2 * rx) * w, by = (X1 - X2 * ry) * w;
+        const float ax = rx * w, ay = ry * w, am = -w;
+        S += (double)(am * am);
+        Sxz += (double)(am * ax);
+        Syz += (double)(am * ay);
+        Szz += (double)(ax * ax) + (double)(ay * ay);
+        b0 += (double)(am * bx);
+        b1 += (double)(am * by);
+        b2 += (double)(ax * bx) + (double)(ay * by);
+      }
+      S = quad_sum_f64(S);
+      Sxz = quad_sum_f64(Sxz);
+      Syz = quad_sum_f64(Syz);
+      Szz = quad_sum_f64(Szz);
+      b0 = quad_sum_f64(b0);
+      b1 = quad_sum_f64(b1);
+      b2 = quad_sum_f64(b2);
+      const double iS = 1.0 / S;
+      const double den = Szz - (Sxz * Sxz + Syz * Syz) * iS;
+      const double tz = (b2 - (Sxz * b0 + Syz * b1) * iS) / den;
+      T0 = (float)((b0 - Sxz * tz) * iS);
+      T1 = (float)((b1 - Syz * tz) * iS);
+      T2 = (float)tz;
+      if (T2 < 0.f) {  // T[T_z < 0] *= -1  (:93)
+        T0 = -T0;
+        T1 = -T1;
+        T2 = -T2;
+      }
+      if (live && q == 0) {
+        ts[pl * 3 + 0] = T0;
+        ts[pl * 3 + 1] = T1;
+        ts[pl * 3 + 2] = T2;
+      }
+    } else {
+      T0 = ts[pp * 3 + 0];
+      T1 = ts[pp * 3 + 1];
+      T2 = ts[pp * 3 + 2];
+    }
+    if (live) {
+      float* gp = g_out != nullptr ? g_out + (p0 + pl) * D : nullptr;
+      for (int j = q; j < J; j += kGeomTpp) {
+        const float2 p2 = up[j];
+        float rx = Ki[0] * p2.x + Ki[1] * p2.y + Ki[2];
+        float ry = Ki[3] * p2.x + Ki[4] * p2.y + Ki[5];
+        float rz = Ki[6] * p2.x + Ki[7] * p2.y + Ki[8];
+        rx = rx / rz;
+        ry = ry / rz;
+        rz = rz / rz;
+        const float nrm = sqrtf(rx * rx + ry * ry + rz * rz);
+        const float hx = rx / nrm, hy = ry / nrm, hz = rz / nrm;
+        const float X0 = xp[3 * j], X1 = xp[3 * j + 1], X2 = xp[3 * j + 2];
+        const float q0 = X0 + T0, q1 = X1 + T1, q2 = X2 + T2;
+        const float d = q0 * hx + q1 * hy + q2 * hz;
+        const float g0 = d * hx - q0, g1 = d * hy - q1, g2 = d * hz - q2;
+        if (gp != nullptr) {
+          gp[3 * j] = g0;
+          gp[3 * j + 1] = g1;
+          gp[3 * j + 2] = g2;
+        }
+        xp[3 * j] = X0 + g0;
+        xp[3 * j + 1] = X1 + g1;
+        xp[3 * j + 2] = X2 + g2;
+      }
+    }
+  }
+  __syncthreads();
+
+  if (x_out != nullptr) {
+    float* og = x_out + p0 * D;
+    for_block_elems(n, D, [&](int i, int r, int c) { og[i] = xs[r * Dp + c]; });
+  }
+  if (solve_T)
+    for (int i = tid; i < n * 3; i += kGeomThreads) T[p0 * 3 + i] = ts[i];
+  if (xa != nullptr) {
+    // rows p0 .. p0 + n of the first GEMM's A operand: 64 halves per row (3J padded with zeros), hi and lo;
+    // consecutive threads write consecutive 16-byte chunks of the blocked layout
+    for (int item = tid; item < kGeomPoses * (kBlockK / 8); item += kGeomThreads) {
+      const int r = item & (kGeomPoses - 1), ch = item / kGeomPoses;
+      if (r >= n) continue;
+      const float* xp = xs + r * Dp;
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c0 = ch * 8 + 2 * e;
+        const float a = c0 < D ? xp[c0] : 0.f;
+        const float b = c0 + 1 < D ? xp[c0 + 1] : 0.f;
+        __half h0, l0, h1, l1;
+        split_hi_lo(a, h0, l0);
+        split_hi_lo(b, h1, l1);
+        hi[e] = pack_half2(h0, h1);
+        lo[e] = pack_half2(l0, l1);
+      }
+      *reinterpret_cast<uint4*>(xa + blocked_half_offset(p0 + r, ch * 8, kBlockK, kActTileRows, 0)) =
+          make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(xa + blocked_half_offset(p0 + r, ch * 8, kBlockK, kActTileRows, 1)) =
+          make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
 // x [B, D] float32 -> blocked hi/lo A operand of the first GEMM (one k-block of 64 columns)
 __global__ void pack_x_kernel(const float* __restrict__ x, __half* __restrict__ xa, int64_t B, int D) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -246,8 +457,25 @@ int launch_grad_field(const float* uv, const float* x, const float* K, float* co
   } else {
     eps_prev = nullptr;
   }
-  ZEDO_CUDA_TRY(launch_pdl(grad_field_kernel, dim3((unsigned)blocks), dim3(kGeomWarps * 32), 0, st, uv, x, K, conf, T,
-                           solve_T, clamp_inplace, g, x_out, xa, B, J, eps_prev, nhb, g2, sd, dt, dump));
+  // ZEDO_GEOM=warp|block forces one kernel (tests); default: 128-pose CTAs once the batch fills the GPU
+  const char* env = getenv("ZEDO_GEOM");
+  const int forced = env == nullptr ? 0 : (strcmp(env, "warp") == 0 ? 1 : (strcmp(env, "block") == 0 ? 2 : 0));
+  const bool block = forced == 2 || (forced == 0 && B >= kGeomBlockMinPoses);
+  if (block) {
+    const size_t smem = (size_t)geom_block_smem_floats(J) * sizeof(float);
+    static int attr_smem = 0;
+    if ((int)smem > attr_smem) {
+      ZEDO_CUDA_TRY(cudaFuncSetAttribute(grad_field_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+      attr_smem = (int)smem;
+    }
+    const int64_t nb = (B + kGeomPoses - 1) / kGeomPoses;
+    ZEDO_CUDA_TRY(launch_pdl(grad_field_block_kernel, dim3((unsigned)nb), dim3(kGeomThreads), smem, st, uv, x, K, conf,
+                             T, solve_T, clamp_inplace, g, x_out, xa, B, J, eps_prev, nhb, g2, sd, dt, dump));
+  } else {
+    ZEDO_CUDA_TRY(launch_pdl(grad_field_kernel, dim3((unsigned)blocks), dim3(kGeomWarps * 32), 0, st, uv, x, K, conf,
+                             T, solve_T, clamp_inplace, g, x_out, xa, B, J, eps_prev, nhb, g2, sd, dt, dump));
+  }
   ZEDO_LAUNCH_CHECK();
   return 0;
 }
