@@ -165,6 +165,12 @@ int zedo_eval_multi(const float* pred, const double* gt, int32_t protocol2, int6
 int zedo_pck_counts(const float* pred, const double* gt, const int32_t* select, int64_t N, int32_t S,
                     int32_t J, const int32_t* joint_subset, int32_t n_sub, uint64_t* counts, void* stream);
 
+/* Diversity of the hypotheses.  Replaces the "std" report of lib/dataset/mpii3dHP.py:487-490:
+ * multi_preds_cam - multi_preds_cam[:, :, [0], :], root dropped, .std(axis=1) over the S hypotheses.
+ * out_std: device float64 [N, J-1, 3] (population std, ddof = 0); the reference prints its mean over
+ * poses and joints per coordinate. */
+int zedo_hypothesis_std(const float* pred, int64_t N, int32_t S, int32_t J, double* out_std, void* stream);
+
 /* ---- misc ---------------------------------------------------------------------------------------- */
 const char* zedo_strerror(int code);
 int zedo_abi_version(void);

@@ -608,13 +608,23 @@ def compute_auc(gts, preds, eval_joints=None):
     return float(np.mean([compute_pck(gts, preds, eval_joints, t) for t in np.linspace(0, 150, 31)]))
 
 
-def eval_multi(preds, gts, protocol2=False, actions=None, joint_subset=None):
+def hypothesis_std(preds):
+    """Diversity report of mpii3dHP.py:487-490: ``multi_preds_cam - multi_preds_cam[:, :, [0], :]``, root
+    dropped, ``[..., c].std(axis=1).mean()`` for c = x, y, z.  preds [N,S,J,3] -> 3 floats."""
+    rel = (preds - preds[:, :, [0], :])[:, :, 1:, :]
+    return tuple(float(rel[..., c].std(axis=1).mean()) for c in range(3))
+
+
+def eval_multi(preds, gts, protocol2=False, actions=None, joint_subset=None, valid_ind=None):
     """Multi-hypothesis evaluation (h36m.py:365-442; pw3d.py:286-345 for the plain mean).
 
     preds [N,S,J,3]; gts [N,J,3] already root-relative in metres.  Per pose: error of
     every hypothesis (optionally after Procrustes), ``np.argmin`` / ``np.amin`` over S.
     actions: optional int[N] in 2..16 -> H36M aggregate = mean over the 15 action means
     (h36m.py:424-433); otherwise the plain mean over poses.
+    valid_ind: optional per-pose collections of admissible hypothesis indices (h36m.py:399-401): the
+    others are skipped, and the returned index counts inside the kept list, as ``np.argmin`` of the
+    reference's filtered ``multi_results`` does.
     Returns (aggregate, per_pose_min [N], argmin [N]).
     """
     N, S = preds.shape[:2]
@@ -624,6 +634,8 @@ def eval_multi(preds, gts, protocol2=False, actions=None, joint_subset=None):
         gt = gts[n]
         errs = []
         for s in range(S):
+            if valid_ind is not None and s not in valid_ind[n]:
+                continue
             pred = preds[n, s]
             if protocol2:
                 pred = procrustes_align(pred, gt)

@@ -167,6 +167,41 @@ def test_dataset_eval_multi_and_align_to_gt(lib, golden):
         assert np.abs(align_to_gt(g["preds"][n, s], g["gts"][n]) - g["aligned"][k]).max() < 5e-7
 
 
+def test_dataset_eval_variants(lib, golden):
+    """valid_ind filtering, the literal sample_interval semantics and the 3DHP extras (PCK / AUC / std)."""
+    from lib.dataset.synthetic import ArrayPoseDataset
+    g = golden("eval")
+    preds, gts = g["preds"], g["gts"]
+    N, S = preds.shape[:2]
+    zeros2d, zerosK = np.zeros((N, 17, 3), np.float32), np.zeros((N, 3, 3), np.float32)
+    rng = np.random.default_rng(5)
+    valid = [sorted(rng.choice(S, size=rng.integers(1, S + 1), replace=False).tolist()) for _ in range(N)]
+    plain = ArrayPoseDataset(gts, zeros2d, zerosK)
+    h36m = ArrayPoseDataset(gts, zeros2d, zerosK, actions=g["actions"])
+    for p2 in (False, True):
+        agg, res, idx = zo.eval_multi(preds, gts, protocol2=p2, valid_ind=valid)
+        assert abs(plain.eval_multi(preds, protocol2=p2, valid_ind=valid) - agg) < 2e-7
+        assert np.array_equal(plain.last_index, idx)
+        agg_a, _, _ = zo.eval_multi(preds, gts, protocol2=p2, actions=g["actions"], valid_ind=valid)
+        assert abs(h36m.eval_multi(preds, protocol2=p2, valid_ind=valid) - agg_a) < 2e-7
+    with pytest.raises(ValueError):
+        plain.eval_multi(preds, valid_ind=[[]] * N)
+    # sample_interval: preds[::k] against the first len(preds[::k]) ground truths, as the reference does
+    agg3, _, idx3 = zo.eval_multi(preds[::3], gts[:len(preds[::3])])
+    assert abs(plain.eval_multi(preds, sample_interval=3) - agg3) < 2e-7 and np.array_equal(plain.last_index, idx3)
+    with pytest.raises(IndexError):
+        h36m.eval_multi(preds, sample_interval=3)
+    assert abs(h36m.eval_multi(preds, sample_interval=1) - float(g["agg_p0"])) < 2e-7
+    # 3DHP: PCK / AUC of the selected (unaligned) hypotheses and the diversity std
+    hp = ArrayPoseDataset(gts, zeros2d, zerosK, name="3dhp")
+    hp.eval_multi(preds, protocol2=False)
+    _, _, idx = zo.eval_multi(preds, gts)
+    best = preds[np.arange(N), idx]
+    assert abs(hp.last_pck - zo.compute_pck(gts, best)) < 1e-9 and abs(hp.last_auc - zo.compute_auc(gts, best)) < 1e-9
+    assert np.allclose(hp.last_std, zo.hypothesis_std(preds.astype(np.float64)), rtol=1e-9)
+    assert np.allclose(hp.last_std, zo.hypothesis_std(preds), rtol=1e-4)  # the reference's float32 arithmetic
+
+
 def test_control_model_through_the_mirror(lib, golden):
     from lib.algorithms.advanced.control_model import Control_ScoreModelFC_Adv
     from lib.algorithms.advanced import utils as mutils, sde_lib
@@ -186,3 +221,50 @@ def test_control_model_through_the_mirror(lib, golden):
     score = mutils.get_score_fn(sde, m, train=False, continuous=True)(x, torch.ones(8, device="cuda") * 0.05, None, None)
     ref = -zo.control_score_forward(W, g["x"], np.float32(0.05) * np.float32(999)) / zo.subvp_marginal_std(np.float32(0.05))
     assert rel_err(score.cpu().numpy(), ref) < 1e-4
+
+
+def test_checkpoint_file_in_the_reference_format(lib, golden, tmp_path):
+    """run/opt_main.py:120-137 verbatim: torch.load -> strip `module.` -> model.load_state_dict ->
+    ema.load_state_dict -> state['step']; the file is written the way the reference's trainer saves it
+    (DataParallel-prefixed keys, EMA shadow parameters, step)."""
+    import copy
+    import os
+    from lib.algorithms.advanced.model import ScoreModelFC_Adv
+    from lib.algorithms.ema import ExponentialMovingAverage
+    config = ref_config()
+    trained = {k: torch.tensor(v) for k, v in zo.make_weights(seed=0).items()}
+    src = ScoreModelFC_Adv(config, n_joints=17, joint_dim=3, hidden_dim=1024, embed_dim=512, cond_dim=3)
+    trained["sigmas"] = src.sigmas.clone()
+    src.load_state_dict(trained)
+    src_ema = ExponentialMovingAverage(src.parameters(), decay=config.model.ema_rate)
+    src_ema.update(src.parameters())
+    ckpt_path = os.path.join(tmp_path, "checkpoint_1500.pth")
+    torch.save({"model_state_dict": {"module." + k: v for k, v in src.state_dict().items()},
+                "ema": src_ema.state_dict(), "step": 1500, "optimizer": {}}, ckpt_path)
+
+    model = ScoreModelFC_Adv(config, n_joints=17, joint_dim=3, hidden_dim=1024, embed_dim=512, cond_dim=3)
+    model.to(config.device)
+    ema = ExponentialMovingAverage(model.parameters(), decay=config.model.ema_rate)
+    state = dict(optimizer=None, model=model, ema=ema, step=0)
+    old_checkpoint = torch.load(ckpt_path, map_location={'cuda:0': 'cuda:0'})
+    checkpoint = copy.deepcopy(old_checkpoint)
+    checkpoint['model_state_dict'] = {}
+    for k, v in old_checkpoint['model_state_dict'].items():
+        name = k[7:]  # remove `module.`
+        checkpoint['model_state_dict'][name] = v
+    model.load_state_dict(checkpoint['model_state_dict'])
+    ema.load_state_dict(checkpoint['ema'])
+    state['step'] = checkpoint['step']
+    model.eval()
+
+    assert state['step'] == 1500 and ema.num_updates == 1 and ema.decay == config.model.ema_rate
+    assert len(ema.shadow_params) == len(list(model.parameters()))
+    g = golden("net")
+    out = model(torch.tensor(g["x"], device="cuda"), torch.ones(8, device="cuda") * 99.9, None, None)
+    assert rel_err(out.cpu().numpy(), g["out_0.1"]) < 2e-5
+    # the packed plan also accepts the prefixed names directly (C ABI: zedo_plan_create strips `module.`)
+    import zedo_release_b200 as zr
+    plan = zr.ScorePlan({k: v.cuda() for k, v in old_checkpoint['model_state_dict'].items()}, n_joints=17, max_batch=8)
+    out2 = plan.forward(torch.tensor(g["x"], device="cuda"), 99.9)
+    plan.close()
+    assert torch.equal(out2, out)

@@ -23,6 +23,7 @@ EXPORTS = (
     "zedo_sde_step", "zedo_oil_loop", "zedo_ipo_fit", "zedo_rotopt_forward", "zedo_rotopt_backward",
     "zedo_eval_multi", "zedo_strerror", "zedo_abi_version", "zedo_launch_count", "zedo_subvp_scalars",
     "zedo_blocked_offset", "zedo_plan_profile", "zedo_plan_profile_read", "zedo_ipo_fit_ex", "zedo_pck_counts",
+    "zedo_hypothesis_std",
 )
 
 
@@ -63,6 +64,7 @@ def _load() -> C.CDLL:
         "zedo_rotopt_backward": (C.c_int, [p, p, p, p, p, f32, f32, p, p, p, i64, i32, vp]),
         "zedo_eval_multi": (C.c_int, [p, p, i32, i64, i32, i32, C.POINTER(i32), i32, p, p, p, p, vp]),
         "zedo_pck_counts": (C.c_int, [p, p, p, i64, i32, i32, C.POINTER(i32), i32, p, vp]),
+        "zedo_hypothesis_std": (C.c_int, [p, i64, i32, i32, p, vp]),
         "zedo_strerror": (C.c_char_p, [C.c_int]),
         "zedo_abi_version": (C.c_int, []),
         "zedo_launch_count": (i64, []),

@@ -852,4 +852,11 @@ int zedo_pck_counts(const float* pred, const double* gt, const int32_t* select, 
   return rc;
 }
 
+int zedo_hypothesis_std(const float* pred, int64_t N, int32_t S, int32_t J, double* out_std, void* stream) {
+  if (N == 0 || J == 1) return 0;
+  if (!pred || !out_std) return ZEDO_E_INVALID;
+  if (J < 1 || S < 1 || N < 0) return ZEDO_E_SHAPE;
+  return launch_hypothesis_std(pred, N, S, J, out_std, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -180,6 +180,35 @@ int launch_pck_counts(const float* pred, const double* gt, const int* select, in
   return 0;
 }
 
+// Diversity of the hypotheses (mpii3dHP.py:487-490): root-relative joints 1..J-1, population standard deviation
+// over the S hypotheses of every coordinate.  One thread per (pose, joint, coordinate), two passes, float64.
+__global__ void hypothesis_std_kernel(const float* __restrict__ pred, int64_t N, int S, int J,
+                                      double* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_pose = (J - 1) * 3;
+  if (t >= N * per_pose) return;
+  const int64_t n = t / per_pose;
+  const int e = (int)(t - n * per_pose), j = 1 + e / 3, c = e % 3;
+  const float* base = pred + n * S * J * 3;
+  double mean = 0.0;
+  for (int s = 0; s < S; ++s) mean += (double)base[(s * J + j) * 3 + c] - (double)base[s * J * 3 + c];
+  mean /= S;
+  double var = 0.0;
+  for (int s = 0; s < S; ++s) {
+    const double d = (double)base[(s * J + j) * 3 + c] - (double)base[s * J * 3 + c] - mean;
+    var += d * d;
+  }
+  out[t] = sqrt(var / S);
+}
+
+int launch_hypothesis_std(const float* pred, int64_t N, int S, int J, double* out, cudaStream_t st) {
+  const int64_t total = N * (J - 1) * 3;
+  if (total <= 0) return 0;
+  hypothesis_std_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pred, N, S, J, out);
+  ZEDO_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_eval_multi(const float* pred, const double* gt, int protocol2, int64_t N, int S, int J,
                       const int* subset_dev, int n_sub, double* err_min, int* argmin, double* err_all,
                       double* aligned, cudaStream_t st) {

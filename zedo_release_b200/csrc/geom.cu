@@ -1,16 +1,18 @@
 // K3 / K2: per-step reprojection fit and the fused SDE predictor update.
 //
-// Both geometry kernels restate gradient_field_gen (reference simple_zeroshot_opt.py:46-125):
+// The geometry kernels restate gradient_field_gen (reference simple_zeroshot_opt.py:46-125):
 //   rays r_j = K^-1 [u_j, v_j, 1], r_j /= r_j.z                                     (:61-71)
 //   optional least-squares translation, rows weighted conf^2, sign flip on T_z < 0   (:73-93)
 //   r^_j = r_j/|r_j|; p_j = X_j + T; g_j = (p_j . r^_j) r^_j - p_j                   (:33-36,99,109)
-// Per pose they move x (r/w), uv, conf, K, T = 672 bytes at J = 17 and (optionally) emit the first
-// GEMM's fp16 hi/lo operand in the blocked interleaved layout (common.cuh).
-//   * grad_field_kernel: one warp per pose, lane j owns joint j (J <= 32), xor-shuffle reductions --
-//     lowest latency, used for small batches (it issues ~620 warp instructions per pose).
-//   * grad_field_block_kernel: 128 poses per CTA, inputs staged in shared memory by coalesced loads,
-//     one thread per pose for the serial part (~4x fewer instructions per pose) -- used when the
-//     batch fills the GPU, where the warp kernel is issue-bound rather than HBM-bound.
+// Per pose they move x (r/w), uv, conf, K, T = 672 bytes at J = 17 and (optionally) emit the first GEMM's fp16
+// hi/lo operand in the blocked interleaved layout (common.cuh).  Two kernels, one arithmetic:
+//   * grad_field_warp_kernel: one warp per pose, lane j owns joint j (J <= 32) -- lowest latency, small batches;
+//   * grad_field_block_kernel: 128 poses per CTA staged in shared memory by coalesced loads, four threads per
+//     pose (joints q, q+4, ...) -- ~3.5x fewer instructions per pose, used once the batch fills the GPU.
+// Both call the same per-joint functions below, written with explicit-rounding intrinsics (one float32 rounding
+// per reference tensor op, no compiler-chosen FMA contraction) and reduce the normal equations in the same order
+// (stride-4 partial sums, then (p0+p1)+(p2+p3)), so a pose's result is bit-identical in either kernel, at any
+// position in the batch and however the batch is sharded.
 #include <cstdlib>
 #include <cstring>
 
@@ -18,42 +20,152 @@
 
 namespace zedo {
 
-constexpr int kGeomWarps = 8;
-constexpr int64_t kGeomBlockMinPoses = 32768;  // >= 256 CTAs of 128 poses
+constexpr int kGeomWarps = 8;                   // warp kernel: poses per CTA
+constexpr int kGeomPoses = 128;                 // block kernel: poses per CTA
+constexpr int kGeomTpp = 4;                     // block kernel: threads per pose
+constexpr int kGeomThreads = kGeomPoses * kGeomTpp;
+constexpr int64_t kGeomBlockMinPoses = 32768;   // >= 256 CTAs of 128 poses
 
-__device__ __forceinline__ double warp_sum_f64(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+// ---- the arithmetic, shared by both kernels ---------------------------------------------------------------
+// Euler-Maruyama probability-flow update of one coordinate, one rounding per tensor op of sampling.py:185-191 /
+// sde_lib.py:93-100 / utils.py:762-776: score = -eps/std; drift = (-0.5 beta) x - g^2 score; x + drift*dt
+__device__ __forceinline__ float em_pf_update(float xv, float e, float neg_half_beta, float g2, float std, float dt) {
+  const float score = __fdiv_rn(-e, std);
+  const float drift = __fsub_rn(__fmul_rn(neg_half_beta, xv), __fmul_rn(g2, score));
+  return __fadd_rn(xv, __fmul_rn(drift, dt));
+}
+
+// general 3x3 inverse by the adjugate (skew allowed), every product and sum rounded once
+__device__ __forceinline__ float det2_rn(float a, float b, float c, float d) {
+  return __fsub_rn(__fmul_rn(a, d), __fmul_rn(b, c));
+}
+__device__ __forceinline__ void inv3x3_rn(const float* m, float* o) {
+  const float A = det2_rn(m[4], m[5], m[7], m[8]), B = -det2_rn(m[3], m[5], m[6], m[8]);
+  const float C = det2_rn(m[3], m[4], m[6], m[7]);
+  const float det = __fadd_rn(__fadd_rn(__fmul_rn(m[0], A), __fmul_rn(m[1], B)), __fmul_rn(m[2], C));
+  const float r = __fdiv_rn(1.0f, det);
+  o[0] = __fmul_rn(A, r);
+  o[1] = __fmul_rn(-det2_rn(m[1], m[2], m[7], m[8]), r);
+  o[2] = __fmul_rn(det2_rn(m[1], m[2], m[4], m[5]), r);
+  o[3] = __fmul_rn(B, r);
+  o[4] = __fmul_rn(det2_rn(m[0], m[2], m[6], m[8]), r);
+  o[5] = __fmul_rn(-det2_rn(m[0], m[2], m[3], m[5]), r);
+  o[6] = __fmul_rn(C, r);
+  o[7] = __fmul_rn(-det2_rn(m[0], m[1], m[6], m[7]), r);
+  o[8] = __fmul_rn(det2_rn(m[0], m[1], m[3], m[4]), r);
+}
+
+// K^-1 [u, v, 1] (a 3-term dot product accumulated left to right), then ray / ray.z  (:61-71)
+struct Ray {
+  float x, y, z;
+};
+__device__ __forceinline__ Ray back_project(const float* Ki, float u, float v) {
+  Ray r;
+  r.x = __fadd_rn(__fmaf_rn(Ki[1], v, __fmul_rn(Ki[0], u)), Ki[2]);
+  r.y = __fadd_rn(__fmaf_rn(Ki[4], v, __fmul_rn(Ki[3], u)), Ki[5]);
+  const float z = __fadd_rn(__fmaf_rn(Ki[7], v, __fmul_rn(Ki[6], u)), Ki[8]);
+  r.x = __fdiv_rn(r.x, z);
+  r.y = __fdiv_rn(r.y, z);
+  r.z = (z != 0.f && fabsf(z) <= 3.402823466e+38f) ? 1.f : __int_as_float(0x7fc00000);  // == z / z
+  return r;
+}
+
+// One joint's contribution to A^T A and A^T b (:73-90).  The rows of A and b are formed and weighted in float32
+// exactly as the reference forms them; the products of A^T A / A^T b are float32 too (its bmm inputs), but the
+// sums run in float64: the system is ill-conditioned along the depth axis (cond ~ 1e3) and float64 sums + solve
+// return the exact solution of the reference's system, so the kernel differs from the reference only by the
+// reference's own float32 rounding.
+struct NormalEq {
+  double S, Sxz, Syz, Szz, b0, b1, b2;  // M = [[S,0,Sxz],[0,S,Syz],[Sxz,Syz,Szz]], rhs = (b0, b1, b2)
+};
+__device__ __forceinline__ NormalEq joint_normal_eq(const Ray& r, float X0, float X1, float X2, float w) {
+  const float bx = __fmul_rn(__fsub_rn(X0, __fmul_rn(X2, r.x)), w);
+  const float by = __fmul_rn(__fsub_rn(X1, __fmul_rn(X2, r.y)), w);
+  const float ax = __fmul_rn(r.x, w), ay = __fmul_rn(r.y, w), am = -w;
+  NormalEq t;
+  t.S = (double)__fmul_rn(am, am);
+  t.Sxz = (double)__fmul_rn(am, ax);
+  t.Syz = (double)__fmul_rn(am, ay);
+  t.Szz = __dadd_rn((double)__fmul_rn(ax, ax), (double)__fmul_rn(ay, ay));
+  t.b0 = (double)__fmul_rn(am, bx);
+  t.b1 = (double)__fmul_rn(am, by);
+  t.b2 = __dadd_rn((double)__fmul_rn(ax, bx), (double)__fmul_rn(ay, by));
+  return t;
+}
+
+// eliminate the two S rows (Schur complement on the depth axis); T[T_z < 0] *= -1  (:91-93)
+__device__ __forceinline__ void solve_translation(const NormalEq& e, float& T0, float& T1, float& T2) {
+  const double iS = __ddiv_rn(1.0, e.S);
+  const double den = __dsub_rn(e.Szz, __dmul_rn(__dadd_rn(__dmul_rn(e.Sxz, e.Sxz), __dmul_rn(e.Syz, e.Syz)), iS));
+  const double num = __dsub_rn(e.b2, __dmul_rn(__dadd_rn(__dmul_rn(e.Sxz, e.b0), __dmul_rn(e.Syz, e.b1)), iS));
+  const double tz = __ddiv_rn(num, den);
+  T0 = (float)__dmul_rn(__dsub_rn(e.b0, __dmul_rn(e.Sxz, tz)), iS);
+  T1 = (float)__dmul_rn(__dsub_rn(e.b1, __dmul_rn(e.Syz, tz)), iS);
+  T2 = (float)tz;
+  if (T2 < 0.f) {
+    T0 = -T0;
+    T1 = -T1;
+    T2 = -T2;
+  }
+}
+
+// unit ray, p = X + T, g = (p . r^) r^ - p  (:33-36,99,109); returns g, and X + g in n
+__device__ __forceinline__ void project_on_ray(const Ray& r, float X0, float X1, float X2, float T0, float T1,
+                                               float T2, float* g, float* n) {
+  const float nrm =
+      __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(r.x, r.x), __fmul_rn(r.y, r.y)), __fmul_rn(r.z, r.z)));
+  const float hx = __fdiv_rn(r.x, nrm), hy = __fdiv_rn(r.y, nrm), hz = __fdiv_rn(r.z, nrm);
+  const float p0 = __fadd_rn(X0, T0), p1 = __fadd_rn(X1, T1), p2 = __fadd_rn(X2, T2);
+  const float d = __fadd_rn(__fadd_rn(__fmul_rn(p0, hx), __fmul_rn(p1, hy)), __fmul_rn(p2, hz));
+  g[0] = __fsub_rn(__fmul_rn(d, hx), p0);
+  g[1] = __fsub_rn(__fmul_rn(d, hy), p1);
+  g[2] = __fsub_rn(__fmul_rn(d, hz), p2);
+  n[0] = __fadd_rn(X0, g[0]);
+  n[1] = __fadd_rn(X1, g[1]);
+  n[2] = __fadd_rn(X2, g[2]);
+}
+
+__device__ __forceinline__ float clamp_conf(float c) {
+  if (c > 1.f) c = 1.f;        // conf[conf > 1] = 1        (:65)
+  if (c < 1e-4f) c = 1e-4f;    // conf[conf < 1e-4] = 1e-4  (:66)
+  return c;
+}
+
+__device__ __forceinline__ double quad_sum_f64(double v) {  // (p0 + p1) + (p2 + p3) in every lane of a quad
+  v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 2));
   return v;
 }
 
-// Euler-Maruyama probability-flow update of one coordinate, float32 op order of sampling.py:185-191 /
-// sde_lib.py:93-100 / utils.py:762-776: score = -eps/std; drift = (-0.5 beta) x - g^2 score; x + drift*dt
-__device__ __forceinline__ float em_pf_update(float xv, float e, float neg_half_beta, float g2, float std, float dt) {
-  const float score = -e / std;
-  const float drift = neg_half_beta * xv - g2 * score;
-  return xv + drift * dt;
+// ---- one warp per pose ----------------------------------------------------------------------------------------
+// lane j holds joint j's addend (zero beyond J).  Lanes 0..3 accumulate the stride-4 partial sums left to right
+// -- the order in which a thread of the block kernel walks its joints -- then the quad sum; result in every lane.
+__device__ __forceinline__ double warp_sum_quad_order(double v, int J) {
+  double acc = v;
+  for (int o = kGeomTpp; o < J; o += kGeomTpp) acc = __dadd_rn(acc, __shfl_down_sync(0xffffffffu, v, o));
+  acc = quad_sum_f64(acc);
+  return __shfl_sync(0xffffffffu, acc, 0);
 }
 
 __global__ void __launch_bounds__(kGeomWarps * 32)
-grad_field_kernel(const float* __restrict__ uv, const float* x, const float* __restrict__ Kmat,
-                  float* conf, float* T, int solve_T, int clamp_inplace, float* g_out, float* x_out,
-                  __half* __restrict__ xa, int64_t B, int J, const float* __restrict__ eps_prev, float neg_half_beta,
-                  float gsq, float std, float dt, float* __restrict__ dump) {
+grad_field_warp_kernel(const float* __restrict__ uv, const float* x, const float* __restrict__ Kmat, float* conf,
+                       float* T, int solve_T, int clamp_inplace, float* g_out, float* x_out,
+                       __half* __restrict__ xa, int64_t B, int J, const float* __restrict__ eps_prev,
+                       float neg_half_beta, float gsq, float std, float dt, float* __restrict__ dump) {
   __shared__ float stage[kGeomWarps][kBlockK];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int64_t pose = (int64_t)blockIdx.x * kGeomWarps + wib;
-  griddep_wait();  // PDL: x / eps come from the previous kernels (multi-wave grid: dependents launch at exit)
+  griddep_wait();  // PDL: x / eps / T come from the previous kernels
   if (pose >= B) return;
   const bool active = lane < J;
 
-  // intrinsics: lanes 0..8 load one entry each, broadcast, invert (general 3x3: skew allowed)
+  // intrinsics: lanes 0..8 load one entry each, broadcast, invert
   float kv = lane < 9 ? Kmat[pose * 9 + lane] : 0.f;
   float Km[9], Ki[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) Km[i] = __shfl_sync(0xffffffffu, kv, i);
-  inv3x3(Km, Ki);
+  inv3x3_rn(Km, Ki);
 
   float u = 0.f, v = 0.f, X0 = 0.f, X1 = 0.f, X2 = 0.f, c = 1.f;
   if (active) {
@@ -78,47 +190,24 @@ grad_field_kernel(const float* __restrict__ uv, const float* x, const float* __r
       }
     }
     if (conf != nullptr) {
-      c = conf[pose * J + lane];
-      if (c > 1.f) c = 1.f;          // conf[conf > 1] = 1        (:65)
-      if (c < 1e-4f) c = 1e-4f;      // conf[conf < 1e-4] = 1e-4  (:66)
+      c = clamp_conf(conf[pose * J + lane]);
       if (clamp_inplace) conf[pose * J + lane] = c;
     }
   }
-  float rx = Ki[0] * u + Ki[1] * v + Ki[2];
-  float ry = Ki[3] * u + Ki[4] * v + Ki[5];
-  float rz = Ki[6] * u + Ki[7] * v + Ki[8];
-  rx = rx / rz;
-  ry = ry / rz;
-  rz = rz / rz;
+  const Ray ray = back_project(Ki, u, v);
 
   float T0, T1, T2;
   if (solve_T) {
-    const float w = active ? c * c : 0.f;  // row weight conf*conf on A and on b  (:85-88)
-    const float bx = (X0 - X2 * rx) * w, by = (X1 - X2 * ry) * w;
-    const float ax = rx * w, ay = ry * w, am = -w;
-    // The normal equations are ill-conditioned along the depth axis (cond ~ 1e3): the float32 products are
-    // formed exactly as the reference forms them (A and b rows already multiplied by w), but the seven sums
-    // and the 3x3 solve run in float64, so this kernel returns the exact solution of the reference's system
-    // and differs from the reference only by the reference's own float32 rounding.
-    const double S = warp_sum_f64((double)(am * am));
-    const double Sxz = warp_sum_f64((double)(am * ax));
-    const double Syz = warp_sum_f64((double)(am * ay));
-    const double Szz = warp_sum_f64((double)(ax * ax) + (double)(ay * ay));
-    const double b0 = warp_sum_f64((double)(am * bx));
-    const double b1 = warp_sum_f64((double)(am * by));
-    const double b2 = warp_sum_f64((double)(ax * bx) + (double)(ay * by));
-    // M = [[S,0,Sxz],[0,S,Syz],[Sxz,Syz,Szz]]: eliminate the two S rows (Schur complement on the depth axis)
-    const double iS = 1.0 / S;
-    const double den = Szz - (Sxz * Sxz + Syz * Syz) * iS;
-    const double tz = (b2 - (Sxz * b0 + Syz * b1) * iS) / den;
-    T0 = (float)((b0 - Sxz * tz) * iS);
-    T1 = (float)((b1 - Syz * tz) * iS);
-    T2 = (float)tz;
-    if (T2 < 0.f) {  // T[T_z < 0] *= -1  (:93)
-      T0 = -T0;
-      T1 = -T1;
-      T2 = -T2;
-    }
+    // row weight conf*conf on A and on b (:85-88); an idle lane contributes exact zeros
+    NormalEq e = joint_normal_eq(ray, X0, X1, X2, active ? __fmul_rn(c, c) : 0.f);
+    e.S = warp_sum_quad_order(e.S, J);
+    e.Sxz = warp_sum_quad_order(e.Sxz, J);
+    e.Syz = warp_sum_quad_order(e.Syz, J);
+    e.Szz = warp_sum_quad_order(e.Szz, J);
+    e.b0 = warp_sum_quad_order(e.b0, J);
+    e.b1 = warp_sum_quad_order(e.b1, J);
+    e.b2 = warp_sum_quad_order(e.b2, J);
+    solve_translation(e, T0, T1, T2);
     if (lane == 0) {
       T[pose * 3 + 0] = T0;
       T[pose * 3 + 1] = T1;
@@ -131,23 +220,19 @@ grad_field_kernel(const float* __restrict__ uv, const float* x, const float* __r
     T2 = __shfl_sync(0xffffffffu, tv, 2);
   }
 
-  const float nrm = sqrtf(rx * rx + ry * ry + rz * rz);
-  const float hx = rx / nrm, hy = ry / nrm, hz = rz / nrm;
-  const float p0 = X0 + T0, p1 = X1 + T1, p2 = X2 + T2;
-  const float d = p0 * hx + p1 * hy + p2 * hz;
-  const float g0 = d * hx - p0, g1 = d * hy - p1, g2 = d * hz - p2;
-  const float n0 = X0 + g0, n1 = X1 + g1, n2 = X2 + g2;
+  float g[3], n[3];
+  project_on_ray(ray, X0, X1, X2, T0, T1, T2, g, n);
   if (active) {
     const int64_t o = (pose * J + lane) * 3;
     if (g_out != nullptr) {
-      g_out[o] = g0;
-      g_out[o + 1] = g1;
-      g_out[o + 2] = g2;
+      g_out[o] = g[0];
+      g_out[o + 1] = g[1];
+      g_out[o + 2] = g[2];
     }
     if (x_out != nullptr) {
-      x_out[o] = n0;
-      x_out[o + 1] = n1;
-      x_out[o + 2] = n2;
+      x_out[o] = n[0];
+      x_out[o + 1] = n[1];
+      x_out[o + 2] = n[2];
     }
   }
   if (xa != nullptr) {
@@ -157,9 +242,9 @@ grad_field_kernel(const float* __restrict__ uv, const float* x, const float* __r
     st[lane + 32] = 0.f;
     __syncwarp();
     if (active) {
-      st[lane * 3 + 0] = n0;
-      st[lane * 3 + 1] = n1;
-      st[lane * 3 + 2] = n2;
+      st[lane * 3 + 0] = n[0];
+      st[lane * 3 + 1] = n[1];
+      st[lane * 3 + 2] = n[2];
     }
     __syncwarp();
     if (lane < 8) {
@@ -180,16 +265,13 @@ grad_field_kernel(const float* __restrict__ uv, const float* x, const float* __r
   }
 }
 
-// ---- 128 poses per CTA, four threads per pose ----------------------------------------------------------
-constexpr int kGeomPoses = 128;
-constexpr int kGeomTpp = 4;  // threads per pose in the per-pose phase (joints j = q, q + 4, ...)
-constexpr int kGeomThreads = kGeomPoses * kGeomTpp;
-
+// ---- 128 poses per CTA, four threads per pose -------------------------------------------------------------
 // elements i = tid, tid + 512, ... of an [n, len] row-major block: f(i, row, col) without a division per element
 template <class F>
 __device__ __forceinline__ void for_block_elems(int n, int len, F f) {
   int row = (int)threadIdx.x / len, col = (int)threadIdx.x - row * len;
   const int drow = kGeomThreads / len, dcol = kGeomThreads - drow * len;
+#pragma unroll 4  // several independent global loads in flight per thread
   for (int i = threadIdx.x; i < n * len; i += kGeomThreads) {
     f(i, row, col);
     row += drow;
@@ -201,15 +283,9 @@ __device__ __forceinline__ void for_block_elems(int n, int len, F f) {
   }
 }
 
-__host__ __device__ inline int geom_block_smem_floats(int J) {
+__host__ __device__ inline int geom_smem_floats(int J) {
   const int Jp = J | 1, Dp = (3 * J) | 1;  // odd strides keep the per-pose reads spread over the banks
   return kGeomPoses * (2 * Jp + Dp + Jp + 9 + 3);
-}
-
-__device__ __forceinline__ double quad_sum_f64(double v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 1);
-  v += __shfl_xor_sync(0xffffffffu, v, 2);
-  return v;
 }
 
 __global__ void __launch_bounds__(kGeomThreads)
@@ -235,9 +311,7 @@ grad_field_block_kernel(const float* __restrict__ uv, const float* x, const floa
   if (conf != nullptr) {
     float* cg = conf + p0 * J;
     for_block_elems(n, J, [&](int i, int r, int c) {
-      float cv = cg[i];
-      if (cv > 1.f) cv = 1.f;        // conf[conf > 1] = 1        (:65)
-      if (cv < 1e-4f) cv = 1e-4f;    // conf[conf < 1e-4] = 1e-4  (:66)
+      const float cv = clamp_conf(cg[i]);
       if (clamp_inplace) cg[i] = cv;
       cs[r * Jp + c] = cv;
     });
@@ -267,51 +341,34 @@ grad_field_block_kernel(const float* __restrict__ uv, const float* x, const floa
     const bool live = pl < n;
     const int pp = live ? pl : n - 1;
     float Ki[9];
-    inv3x3(ks + pp * 9, Ki);
+    inv3x3_rn(ks + pp * 9, Ki);
     float* xp = xs + pp * Dp;
     const float2* up = us + pp * Jp;
     float T0, T1, T2;
     if (solve_T) {
-      // same float32 products as the reference, float64 sums and solve (see grad_field_kernel)
-      double S = 0, Sxz = 0, Syz = 0, Szz = 0, b0 = 0, b1 = 0, b2 = 0;
+      NormalEq e{0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 4
       for (int j = q; j < J; j += kGeomTpp) {
         const float2 p2 = up[j];
-        float rx = Ki[0] * p2.x + Ki[1] * p2.y + Ki[2];
-        float ry = Ki[3] * p2.x + Ki[4] * p2.y + Ki[5];
-        const float rz = Ki[6] * p2.x + Ki[7] * p2.y + Ki[8];
-        rx = rx / rz;
-        ry = ry / rz;
         const float c = conf != nullptr ? cs[pp * Jp + j] : 1.f;
-        const float w = c * c;
-        const float X0 = xp[3 * j], X1 = xp[3 * j + 1], X2 = xp[3 * j + 2];
-        const float bx = (X0 - X2 * rx) * w, by = (X1 - X2 * ry) * w;
-        const float ax = rx * w, ay = ry * w, am = -w;
-        S += (double)(am * am);
-        Sxz += (double)(am * ax);
-        Syz += (double)(am * ay);
-        Szz += (double)(ax * ax) + (double)(ay * ay);
-        b0 += (double)(am * bx);
-        b1 += (double)(am * by);
-        b2 += (double)(ax * bx) + (double)(ay * by);
+        const NormalEq t = joint_normal_eq(back_project(Ki, p2.x, p2.y), xp[3 * j], xp[3 * j + 1], xp[3 * j + 2],
+                                           __fmul_rn(c, c));
+        e.S = __dadd_rn(e.S, t.S);
+        e.Sxz = __dadd_rn(e.Sxz, t.Sxz);
+        e.Syz = __dadd_rn(e.Syz, t.Syz);
+        e.Szz = __dadd_rn(e.Szz, t.Szz);
+        e.b0 = __dadd_rn(e.b0, t.b0);
+        e.b1 = __dadd_rn(e.b1, t.b1);
+        e.b2 = __dadd_rn(e.b2, t.b2);
       }
-      S = quad_sum_f64(S);
-      Sxz = quad_sum_f64(Sxz);
-      Syz = quad_sum_f64(Syz);
-      Szz = quad_sum_f64(Szz);
-      b0 = quad_sum_f64(b0);
-      b1 = quad_sum_f64(b1);
-      b2 = quad_sum_f64(b2);
-      const double iS = 1.0 / S;
-      const double den = Szz - (Sxz * Sxz + Syz * Syz) * iS;
-      const double tz = (b2 - (Sxz * b0 + Syz * b1) * iS) / den;
-      T0 = (float)((b0 - Sxz * tz) * iS);
-      T1 = (float)((b1 - Syz * tz) * iS);
-      T2 = (float)tz;
-      if (T2 < 0.f) {  // T[T_z < 0] *= -1  (:93)
-        T0 = -T0;
-        T1 = -T1;
-        T2 = -T2;
-      }
+      e.S = quad_sum_f64(e.S);
+      e.Sxz = quad_sum_f64(e.Sxz);
+      e.Syz = quad_sum_f64(e.Syz);
+      e.Szz = quad_sum_f64(e.Szz);
+      e.b0 = quad_sum_f64(e.b0);
+      e.b1 = quad_sum_f64(e.b1);
+      e.b2 = quad_sum_f64(e.b2);
+      solve_translation(e, T0, T1, T2);
       if (live && q == 0) {
         ts[pl * 3 + 0] = T0;
         ts[pl * 3 + 1] = T1;
@@ -324,28 +381,19 @@ grad_field_block_kernel(const float* __restrict__ uv, const float* x, const floa
     }
     if (live) {
       float* gp = g_out != nullptr ? g_out + (p0 + pl) * D : nullptr;
+#pragma unroll 4
       for (int j = q; j < J; j += kGeomTpp) {
         const float2 p2 = up[j];
-        float rx = Ki[0] * p2.x + Ki[1] * p2.y + Ki[2];
-        float ry = Ki[3] * p2.x + Ki[4] * p2.y + Ki[5];
-        float rz = Ki[6] * p2.x + Ki[7] * p2.y + Ki[8];
-        rx = rx / rz;
-        ry = ry / rz;
-        rz = rz / rz;
-        const float nrm = sqrtf(rx * rx + ry * ry + rz * rz);
-        const float hx = rx / nrm, hy = ry / nrm, hz = rz / nrm;
-        const float X0 = xp[3 * j], X1 = xp[3 * j + 1], X2 = xp[3 * j + 2];
-        const float q0 = X0 + T0, q1 = X1 + T1, q2 = X2 + T2;
-        const float d = q0 * hx + q1 * hy + q2 * hz;
-        const float g0 = d * hx - q0, g1 = d * hy - q1, g2 = d * hz - q2;
+        float g[3], nx[3];
+        project_on_ray(back_project(Ki, p2.x, p2.y), xp[3 * j], xp[3 * j + 1], xp[3 * j + 2], T0, T1, T2, g, nx);
         if (gp != nullptr) {
-          gp[3 * j] = g0;
-          gp[3 * j + 1] = g1;
-          gp[3 * j + 2] = g2;
+          gp[3 * j] = g[0];
+          gp[3 * j + 1] = g[1];
+          gp[3 * j + 2] = g[2];
         }
-        xp[3 * j] = X0 + g0;
-        xp[3 * j + 1] = X1 + g1;
-        xp[3 * j + 2] = X2 + g2;
+        xp[3 * j] = nx[0];
+        xp[3 * j + 1] = nx[1];
+        xp[3 * j + 2] = nx[2];
       }
     }
   }
@@ -447,7 +495,6 @@ int launch_grad_field(const float* uv, const float* x, const float* K, float* co
                       int clamp_inplace, float* g, float* x_out, __half* xa, int64_t B, int J, cudaStream_t st,
                       const float* eps_prev, const SdeCoef* prev, float* dump) {
   if (B == 0) return 0;
-  const int64_t blocks = (B + kGeomWarps - 1) / kGeomWarps;
   float nhb = 0.f, g2 = 0.f, sd = 1.f, dt = 0.f;
   if (eps_prev != nullptr && prev != nullptr) {
     nhb = -0.5f * prev->beta_t;
@@ -460,21 +507,21 @@ int launch_grad_field(const float* uv, const float* x, const float* K, float* co
   // ZEDO_GEOM=warp|block forces one kernel (tests); default: 128-pose CTAs once the batch fills the GPU
   const char* env = getenv("ZEDO_GEOM");
   const int forced = env == nullptr ? 0 : (strcmp(env, "warp") == 0 ? 1 : (strcmp(env, "block") == 0 ? 2 : 0));
-  const bool block = forced == 2 || (forced == 0 && B >= kGeomBlockMinPoses);
-  if (block) {
-    const size_t smem = (size_t)geom_block_smem_floats(J) * sizeof(float);
+  if (forced == 2 || (forced == 0 && B >= kGeomBlockMinPoses)) {
+    const size_t smem = (size_t)geom_smem_floats(J) * sizeof(float);
     static int attr_smem = 0;
     if ((int)smem > attr_smem) {
       ZEDO_CUDA_TRY(cudaFuncSetAttribute(grad_field_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
       attr_smem = (int)smem;
     }
-    const int64_t nb = (B + kGeomPoses - 1) / kGeomPoses;
-    ZEDO_CUDA_TRY(launch_pdl(grad_field_block_kernel, dim3((unsigned)nb), dim3(kGeomThreads), smem, st, uv, x, K, conf,
-                             T, solve_T, clamp_inplace, g, x_out, xa, B, J, eps_prev, nhb, g2, sd, dt, dump));
+    ZEDO_CUDA_TRY(launch_pdl(grad_field_block_kernel, dim3((unsigned)((B + kGeomPoses - 1) / kGeomPoses)),
+                             dim3(kGeomThreads), smem, st, uv, x, K, conf, T, solve_T, clamp_inplace, g, x_out, xa, B,
+                             J, eps_prev, nhb, g2, sd, dt, dump));
   } else {
-    ZEDO_CUDA_TRY(launch_pdl(grad_field_kernel, dim3((unsigned)blocks), dim3(kGeomWarps * 32), 0, st, uv, x, K, conf,
-                             T, solve_T, clamp_inplace, g, x_out, xa, B, J, eps_prev, nhb, g2, sd, dt, dump));
+    ZEDO_CUDA_TRY(launch_pdl(grad_field_warp_kernel, dim3((unsigned)((B + kGeomWarps - 1) / kGeomWarps)),
+                             dim3(kGeomWarps * 32), 0, st, uv, x, K, conf, T, solve_T, clamp_inplace, g, x_out, xa, B,
+                             J, eps_prev, nhb, g2, sd, dt, dump));
   }
   ZEDO_LAUNCH_CHECK();
   return 0;

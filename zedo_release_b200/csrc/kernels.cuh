@@ -46,6 +46,7 @@ int launch_rotopt_forward(const float* q, const float* scale, const float* xk, c
 int launch_rotopt_backward(const float* q, const float* scale, const float* xk, const float* T0, const float* K,
                            float minT, float maxT, const float* d_uv, float* d_q, float* d_scale, int64_t B, int nk,
                            cudaStream_t st);
+int launch_hypothesis_std(const float* pred, int64_t N, int S, int J, double* out, cudaStream_t st);
 int launch_pck_counts(const float* pred, const double* gt, const int* select, int64_t N, int S, int J,
                       const int* subset_dev, int n_sub, unsigned long long* counts, cudaStream_t st);
 int launch_eval_multi(const float* pred, const double* gt, int protocol2, int64_t N, int S, int J,

@@ -250,6 +250,18 @@ def pck_auc(pred: torch.Tensor, gt: torch.Tensor, select: Optional[torch.Tensor]
     return float(pcks[30]), float(pcks.mean())
 
 
+def hypothesis_std(pred: torch.Tensor) -> Tuple[float, float, float]:
+    """Diversity of the hypotheses as lib/dataset/mpii3dHP.py:487-490 reports it: per coordinate, the
+    std over the S hypotheses of the root-relative joints 1..J-1, averaged over poses and joints.
+    pred [N,S,J,3] f32 -> (std_x, std_y, std_z)."""
+    pred = _f32(pred, "pred")
+    N, S, J = pred.shape[0], pred.shape[1], pred.shape[2]
+    out = torch.zeros((N, max(J - 1, 0), 3), dtype=torch.float64, device=pred.device)
+    nat.check(nat.lib.zedo_hypothesis_std(_ptr(pred), N, S, J, _ptr(out), _stream()), "zedo_hypothesis_std")
+    m = out.mean(dim=(0, 1)).cpu().numpy() if out.numel() else np.full(3, np.nan)
+    return float(m[0]), float(m[1]), float(m[2])
+
+
 def aggregate_errors(err_min, actions=None) -> float:
     """H36M: mean over actions 2..16 of the per-action means (h36m.py:424-433); otherwise the
     plain mean (pw3d.py:338).  Host-side numpy over the [N] float64 result vector."""

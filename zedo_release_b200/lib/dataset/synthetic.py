@@ -32,21 +32,49 @@ class ArrayPoseDataset:
 
     def eval_multi(self, preds, protocol2=False, print_verbose=False, sample_interval=None, valid_ind=None):
         """preds [N, m, j, 3] -> scalar error in metres; per pose the minimum over the m hypotheses of
-        the mean per-joint error (after Procrustes alignment when protocol2)."""
-        if valid_ind is not None:
-            raise NotImplementedError("valid_ind filtering is not implemented")
+        the mean per-joint error (after Procrustes alignment when protocol2).
+
+        ``valid_ind`` (h36m.py:399-401): per-pose collections of admissible hypothesis indices; the others
+        are skipped and ``last_index`` counts inside the kept list, like the reference's ``np.argmin`` over
+        its filtered list.  ``sample_interval`` keeps the reference's semantics literally (h36m.py:385-386,
+        pw3d.py:296-297): ``preds[::k]`` is compared with the FIRST ``len(preds[::k])`` ground truths, and
+        the action-wise H36M aggregate then indexes the shortened result array with full-length indices,
+        which raises IndexError in the reference as it does here.
+        With ``name='3dhp'`` the 3DHP extras (mpii3dHP.py:480-490) are computed too: ``last_pck``,
+        ``last_auc`` on the selected hypotheses and ``last_std`` (diversity)."""
         assert len(preds) == len(self.db_3d)
         gt = self.db_3d - self.db_3d[:, 0:1]
         actions = self.actions
         if sample_interval is not None:
-            preds, gt = preds[::sample_interval], gt[::sample_interval]
-            actions = None if actions is None else actions[::sample_interval]
+            preds = preds[::sample_interval]
+            gt = gt[:len(preds)]
+            if actions is not None and len(preds) != len(actions):
+                raise IndexError(f"index {len(actions) - 1} is out of bounds for axis 0 with size {len(preds)} "
+                                 "(action-wise aggregate over a sub-sampled result array, h36m.py:430-431)")
         dev = torch.device("cuda", torch.cuda.current_device())
         p = torch.as_tensor(np.ascontiguousarray(preds, dtype=np.float32), device=dev)
         g = torch.as_tensor(np.ascontiguousarray(gt, dtype=np.float64), device=dev)
-        err, idx = engine.eval_multi(p, g, protocol2=protocol2, joint_subset=self.joint_subset)
-        self.last_index = idx.cpu().numpy()
+        if valid_ind is None:
+            err, idx = engine.eval_multi(p, g, protocol2=protocol2, joint_subset=self.joint_subset)
+            sel = idx
+            self.last_index = idx.cpu().numpy()
+        else:
+            _, _, err_all = engine.eval_multi(p, g, protocol2=protocol2, joint_subset=self.joint_subset,
+                                              return_all=True)
+            keep = np.zeros(err_all.shape, dtype=bool)
+            for n, allowed in enumerate(valid_ind):
+                keep[n, [s for s in range(keep.shape[1]) if s in allowed]] = True
+            if not keep.any(axis=1).all():
+                raise ValueError("attempt to get argmin of an empty sequence")  # np.argmin([]) in the reference
+            keep_t = torch.as_tensor(keep, device=dev)
+            masked = torch.where(keep_t, err_all, torch.full_like(err_all, float("inf")))
+            err, sel = masked.min(dim=1)
+            # position of the winner inside the kept list
+            self.last_index = (torch.cumsum(keep_t, dim=1).gather(1, sel[:, None])[:, 0] - 1).cpu().numpy()
         error = engine.aggregate_errors(err, actions)
+        if self.name == "3dhp":
+            self.last_pck, self.last_auc = engine.pck_auc(p, g, select=sel, joint_subset=None)
+            self.last_std = engine.hypothesis_std(p)
         if print_verbose:
             print(f"{self.name} {'p2' if protocol2 else 'p1'}: {error:.5f}")
         return error
