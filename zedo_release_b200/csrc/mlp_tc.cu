@@ -204,7 +204,9 @@ static int launch_ew(const LayerArgs& a, int num_sms, cudaStream_t st) {
 template <int BN, int NPROD, int EPI>
 static int launch_one(const LayerArgs& a, int num_sms, cudaStream_t st) {
   if constexpr (BN >= 256) {
-    if (epi_warps_from_env(BN) == 16) return launch_ew<BN, NPROD, EPI, 16>(a, num_sms, st);
+    static const int first16 = getenv("ZEDO_EW_FIRST") ? atoi(getenv("ZEDO_EW_FIRST")) == 16 : 0;
+    if (epi_warps_from_env(BN) == 16 || (first16 && a.num_kb == 1))
+      return launch_ew<BN, NPROD, EPI, 16>(a, num_sms, st);
   }
   return launch_ew<BN, NPROD, EPI, 8>(a, num_sms, st);
 }

@@ -160,6 +160,16 @@ __device__ __forceinline__ void add_hi_lo(float* v, const uint4& h4, const uint4
 }
 
 
+// SiLU y / (1 + e^-y) on the MUFU pipe: ex2.approx.ftz + rcp.approx (2 ulp each).  The .ftz form drops the
+// range check / rescale pair the compiler wraps around a non-ftz ex2 (3 of ~22 instructions per element of the
+// epilogue); it differs only where e^-y is denormal (y > 87), where 1 + e^-y rounds to 1 either way.
+__device__ __forceinline__ float silu_fast(float y) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(y * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return y * r;
+}
+
 // EW epilogue warps per CTA (8 or 16): EW/4 warps share a TMEM lane quarter and split the tile's columns
 constexpr int tc_threads(int ew) { return 64 + ew * 32; }  // producer warp + MMA warp + epilogue warps
 inline int epi_warps_from_env(int bn) {
@@ -259,7 +269,7 @@ __device__ __forceinline__ void epilogue_tile(const LayerArgs& args, uint32_t tm
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float y = fmaf(v[4 * i + e] * rstd, ga[e], be[e]);
-          v[4 * i + e] = __fdividef(y, 1.f + __expf(-y));
+          v[4 * i + e] = silu_fast(y);
         }
       }
     }
