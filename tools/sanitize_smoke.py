@@ -17,6 +17,7 @@ for kind, W in ((nat.NET_SCORE_FC_ADV, zo.make_weights(0)), (nat.NET_CONTROL, zo
     res = zr.run_pose_optimisation(plan, t(ds["db_2d"]), t(ds["camera_param"]), t(ds["clusters"]), cfg, hypo=2, steps=3)
     e, i = zr.eval_multi(res, t(ds["db_3d"], torch.float64), protocol2=True)
     zr.pck_auc(res, t(ds["db_3d"], torch.float64), select=i)
+    zr.hypothesis_std(res)
     torch.cuda.synchronize()
     plan.close()
 big = zr.ScorePlan(zo.make_weights(0), n_joints=17, max_batch=4096, device=0)  # CTA-pair path (more than 18 row tiles)
