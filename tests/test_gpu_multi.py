@@ -61,3 +61,37 @@ def test_sharded_run_equals_single_gpu(tmp_path):
     plan.close()
     assert np.array_equal(got["res"], res.cpu().numpy())  # rows are independent: sharding changes nothing
     assert np.array_equal(got["idx"], idx.cpu().numpy()) and np.array_equal(got["err"], err.cpu().numpy())
+
+
+def test_plan_on_a_non_current_device():
+    """One process, two devices: a plan built for cuda:1 while cuda:0 is current leaves the current device alone,
+    computes on cuda:1 through the engine, and the raw C ABI refuses a call made with the wrong device current."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import ctypes as C
+    import zedo_release_b200 as zr
+    from zedo_release_b200 import _native as nat
+    torch.cuda.set_device(0)
+    W = zo.make_weights(seed=0)
+    x = np.random.default_rng(0).normal(0, 0.3, (300, 17, 3)).astype(np.float32)
+    p0 = zr.ScorePlan(W, n_joints=17, max_batch=300, device=0)
+    p1 = zr.ScorePlan(W, n_joints=17, max_batch=300, device=1)
+    assert torch.cuda.current_device() == 0
+    y0 = p0.forward(torch.tensor(x, device="cuda:0"), 50.0)
+    x1 = torch.tensor(x, device="cuda:1")
+    y1 = p1.forward(x1, 50.0)
+    assert y1.device.index == 1 and torch.cuda.current_device() == 0
+    assert torch.equal(y0.cpu(), y1.cpu())
+    ds = zo.make_synthetic_dataset(300, seed=1)
+    g1, T1 = zr.grad_field(torch.tensor(ds["db_2d"][:, :, :2], device="cuda:1"), x1,
+                           torch.tensor(ds["camera_param"], device="cuda:1"))
+    g0, T0 = zr.grad_field(torch.tensor(ds["db_2d"][:, :, :2], device="cuda:0"), torch.tensor(x, device="cuda:0"),
+                           torch.tensor(ds["camera_param"], device="cuda:0"))
+    assert g1.device.index == 1 and torch.equal(g0.cpu(), g1.cpu()) and torch.equal(T0.cpu(), T1.cpu())
+    out = torch.empty_like(x1)
+    rc = nat.lib.zedo_score_forward(p1._h, C.c_void_p(x1.data_ptr()), 50.0, C.c_void_p(out.data_ptr()), 300, 0,
+                                    C.c_void_p(0))  # cuda:0 is current
+    assert rc == -5  # ZEDO_E_STATE (include/zedo_b200.h)
+    p0.close()
+    p1.close()
+    assert torch.cuda.current_device() == 0

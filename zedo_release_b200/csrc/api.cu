@@ -66,7 +66,12 @@ static int pack_weight(const float* w, int N, int K, int bn, PackedWeight* out) 
     }
   }
   ZEDO_CUDA_TRY(cudaMalloc(&out->dev, buf.size() * sizeof(__half)));
-  ZEDO_CUDA_TRY(cudaMemcpy(out->dev, buf.data(), buf.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  const cudaError_t e = cudaMemcpy(out->dev, buf.data(), buf.size() * sizeof(__half), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(out->dev);
+    out->dev = nullptr;
+    return (int)e;
+  }
   out->descale = 1.f / s;
   out->n_pad = n_pad;
   out->k_pad = k_pad;
@@ -146,6 +151,34 @@ struct zedo_plan {
 };
 
 namespace {
+// plan construction / destruction run on the plan's device and leave the caller's current device as it was
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err;
+  explicit DeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// a short host int array on the device for the duration of one launch (stream-ordered allocation)
+struct StreamInts {
+  int* dev = nullptr;
+  cudaStream_t st;
+  explicit StreamInts(cudaStream_t s) : st(s) {}
+  int put(const int32_t* host, int n) {
+    ZEDO_CUDA_TRY(cudaMallocAsync((void**)&dev, (size_t)n * sizeof(int), st));
+    ZEDO_CUDA_TRY(cudaMemcpyAsync(dev, host, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+    return 0;
+  }
+  ~StreamInts() {
+    if (dev) cudaFreeAsync(dev, st);
+  }
+};
+
 // brackets one launch with events when profiling is on and this launch is sampled
 struct ProfScope {
   zedo_plan* p;
@@ -157,7 +190,11 @@ struct ProfScope {
     if (!p->prof_on) return;
     const int seen = p->prof_seen[kind]++;
     if (seen % p->prof_stride != 0 || p->prof[kind].size() >= 256) return;
-    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+    if (cudaEventCreate(&a) != cudaSuccess) return;
+    if (cudaEventCreate(&b) != cudaSuccess) {
+      cudaEventDestroy(a);
+      return;
+    }
     active = true;
     cudaEventRecord(a, st);
   }
@@ -351,6 +388,9 @@ int net_forward(zedo_plan* p, const float* x, const float* tbl, int64_t B, int m
 int check_batch(const zedo_plan* p, int64_t B) {
   if (p == nullptr) return ZEDO_E_INVALID;
   if (B < 0 || B > p->cap) return ZEDO_E_SHAPE;
+  int cur = -1;
+  ZEDO_CUDA_TRY(cudaGetDevice(&cur));
+  if (cur != p->device) return ZEDO_E_STATE;  // a plan is bound to its device: launches go to the current one
   return 0;
 }
 
@@ -398,7 +438,8 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
   if (desc->n_joints < 1 || desc->n_joints > 21 || D > 64 || H != 1024 || E < 16 || E % 16 != 0 || NB < 1 ||
       NB > 8 || max_batch < 1)
     return ZEDO_E_SHAPE;
-  ZEDO_CUDA_TRY(cudaSetDevice(device));
+  DeviceGuard on_device(device);
+  if (on_device.err != cudaSuccess) return (int)on_device.err;
   zedo_plan* p = new (std::nothrow) zedo_plan();
   if (!p) return ZEDO_E_NOMEM;
   p->desc = *desc;
@@ -632,7 +673,7 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
   PLAN_TRY(dev_alloc(p, &p->eps, (size_t)p->m_pad * 64));
   PLAN_TRY(dev_alloc(p, &p->x32, (size_t)p->m_pad * D));
   PLAN_TRY(ensure_tables(p, 1));
-  ZEDO_CUDA_TRY(cudaDeviceSynchronize());
+  PLAN_TRY((int)cudaDeviceSynchronize());
 #undef NEED
 #undef ADD_W
 #undef ADD_GN
@@ -674,7 +715,7 @@ int zedo_plan_profile_read(zedo_plan* plan, int32_t kind, float* mean_ms, int32_
 
 int zedo_plan_destroy(zedo_plan* plan) {
   if (!plan) return 0;
-  cudaSetDevice(plan->device);
+  DeviceGuard on_device(plan->device);
   cudaDeviceSynchronize();
   zedo_plan_profile(plan, 0, 1);
   for (void* q : plan->owned) cudaFree(q);
@@ -729,6 +770,9 @@ int zedo_oil_loop(zedo_plan* plan, float* x, float* T, const float* uv, const fl
   if (rc) return rc;
   if (!x || !T || !uv || !K || !t_sched || steps < 0 || n_scales < 1) return ZEDO_E_INVALID;
   if (n_dump > 0 && (!dump || !dump_steps)) return ZEDO_E_INVALID;
+  for (int k = 0; k < n_dump; ++k)
+    if (dump_steps[k] < 0 || dump_steps[k] >= steps || (k > 0 && dump_steps[k] < dump_steps[k - 1]))
+      return ZEDO_E_INVALID;  // ascending, inside the schedule
   if (B == 0 || steps == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int J = plan->desc.n_joints, D = plan->D;
@@ -785,13 +829,11 @@ int zedo_ipo_fit_ex(const float* x0, const float* uv, const float* K, const int3
   for (int i = 0; i < nkey; ++i)
     if (keylist[i] < 0 || keylist[i] >= J) return ZEDO_E_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
-  int* kl = nullptr;
-  ZEDO_CUDA_TRY(cudaMallocAsync((void**)&kl, (size_t)nkey * sizeof(int), st));
-  ZEDO_CUDA_TRY(cudaMemcpyAsync(kl, keylist, (size_t)nkey * sizeof(int), cudaMemcpyHostToDevice, st));
-  int rc = launch_ipo_fit(x0, uv, K, kl, nkey, axes_mask, pelvis_a, pelvis_b, ray_init, ipo_T, minT, maxT, iters,
-                          B_global, lr, R, T, x_rot, qs, B, J, st);
-  cudaFreeAsync(kl, st);
-  return rc;
+  StreamInts kl(st);
+  int rc = kl.put(keylist, nkey);
+  if (rc) return rc;
+  return launch_ipo_fit(x0, uv, K, kl.dev, nkey, axes_mask, pelvis_a, pelvis_b, ray_init, ipo_T, minT, maxT, iters,
+                        B_global, lr, R, T, x_rot, qs, B, J, st);
 }
 
 int zedo_ipo_fit(const float* x0, const float* uv, const float* K, const int32_t* keylist, int32_t nkey,
@@ -823,15 +865,13 @@ int zedo_eval_multi(const float* pred, const double* gt, int32_t protocol2, int6
   if (!pred || !gt || !err_min || !argmin) return ZEDO_E_INVALID;
   if (J < 1 || J > 32 || S < 1 || N < 0) return ZEDO_E_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
-  int* sub = nullptr;
+  StreamInts sub(st);
   if (joint_subset != nullptr) {
     if (n_sub < 1 || n_sub > J) return ZEDO_E_SHAPE;
-    ZEDO_CUDA_TRY(cudaMallocAsync((void**)&sub, (size_t)n_sub * sizeof(int), st));
-    ZEDO_CUDA_TRY(cudaMemcpyAsync(sub, joint_subset, (size_t)n_sub * sizeof(int), cudaMemcpyHostToDevice, st));
+    const int rc = sub.put(joint_subset, n_sub);
+    if (rc) return rc;
   }
-  int rc = launch_eval_multi(pred, gt, protocol2, N, S, J, sub, n_sub, err_min, argmin, err_all, aligned, st);
-  if (sub) cudaFreeAsync(sub, st);
-  return rc;
+  return launch_eval_multi(pred, gt, protocol2, N, S, J, sub.dev, n_sub, err_min, argmin, err_all, aligned, st);
 }
 
 int zedo_pck_counts(const float* pred, const double* gt, const int32_t* select, int64_t N, int32_t S, int32_t J,
@@ -840,16 +880,14 @@ int zedo_pck_counts(const float* pred, const double* gt, const int32_t* select, 
   if (!pred || !gt || !counts) return ZEDO_E_INVALID;
   if (J < 1 || J > 32 || S < 1 || N < 0) return ZEDO_E_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
-  int* sub = nullptr;
+  StreamInts sub(st);
   if (joint_subset != nullptr) {
     if (n_sub < 1 || n_sub > J) return ZEDO_E_SHAPE;
-    ZEDO_CUDA_TRY(cudaMallocAsync((void**)&sub, (size_t)n_sub * sizeof(int), st));
-    ZEDO_CUDA_TRY(cudaMemcpyAsync(sub, joint_subset, (size_t)n_sub * sizeof(int), cudaMemcpyHostToDevice, st));
+    const int rc = sub.put(joint_subset, n_sub);
+    if (rc) return rc;
   }
   ZEDO_CUDA_TRY(cudaMemsetAsync(counts, 0, 31 * sizeof(uint64_t), st));
-  int rc = launch_pck_counts(pred, gt, select, N, S, J, sub, n_sub, (unsigned long long*)counts, st);
-  if (sub) cudaFreeAsync(sub, st);
-  return rc;
+  return launch_pck_counts(pred, gt, select, N, S, J, sub.dev, n_sub, (unsigned long long*)counts, st);
 }
 
 int zedo_hypothesis_std(const float* pred, int64_t N, int32_t S, int32_t J, double* out_std, void* stream) {

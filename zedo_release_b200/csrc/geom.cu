@@ -509,12 +509,10 @@ int launch_grad_field(const float* uv, const float* x, const float* K, float* co
   const int forced = env == nullptr ? 0 : (strcmp(env, "warp") == 0 ? 1 : (strcmp(env, "block") == 0 ? 2 : 0));
   if (forced == 2 || (forced == 0 && B >= kGeomBlockMinPoses)) {
     const size_t smem = (size_t)geom_smem_floats(J) * sizeof(float);
-    static int attr_smem = 0;
-    if ((int)smem > attr_smem) {
+    // per call, not cached: the attribute is per device and a process may drive several devices
+    if (smem > 48 * 1024)
       ZEDO_CUDA_TRY(cudaFuncSetAttribute(grad_field_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
-      attr_smem = (int)smem;
-    }
     ZEDO_CUDA_TRY(launch_pdl(grad_field_block_kernel, dim3((unsigned)((B + kGeomPoses - 1) / kGeomPoses)),
                              dim3(kGeomThreads), smem, st, uv, x, K, conf, T, solve_T, clamp_inplace, g, x_out, xa, B,
                              J, eps_prev, nhb, g2, sd, dt, dump));

@@ -7,6 +7,7 @@ arithmetic operation of the path runs in the hand-written sm_100a kernels behind
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from typing import Dict, Iterable, Optional, Sequence, Tuple
 
 import numpy as np
@@ -19,6 +20,21 @@ GEMM_MODES = {"split3": nat.GEMM_SPLIT3, "split2": nat.GEMM_SPLIT2, "fp16": nat.
 
 def _mode(mode) -> int:
     return GEMM_MODES[mode] if isinstance(mode, str) else int(mode)
+
+
+def _device_scoped(fn):
+    """Run ``fn`` with the device of its plan / first CUDA tensor argument current: the C ABI launches on the
+    current device, on the stream ``_stream()`` reads from torch for that device."""
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        for a in list(args) + list(kwargs.values()):
+            dev = a.device if isinstance(a, ScorePlan) else (a.device.index if isinstance(a, torch.Tensor) and a.is_cuda
+                                                             else None)
+            if dev is not None:
+                with torch.cuda.device(dev):
+                    return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+    return wrapped
 
 
 def _stream() -> C.c_void_p:
@@ -78,6 +94,7 @@ class ScorePlan:
     def profile(self, enable: bool, stride: int = 1) -> None:
         nat.check(nat.lib.zedo_plan_profile(self._h, int(bool(enable)), int(stride)), "zedo_plan_profile")
 
+    @_device_scoped
     def profile_read(self) -> Dict[str, Tuple[float, int]]:
         out = {}
         for name, k in self.PROFILE_KINDS.items():
@@ -87,6 +104,7 @@ class ScorePlan:
         return out
 
     # -- ScoreModelFC_Adv.forward (model.py:215-298) --------------------------------------------
+    @_device_scoped
     def forward(self, x: torch.Tensor, t999: float, mode="split3") -> torch.Tensor:
         x = _f32(x, "x")
         B = x.shape[0]
@@ -96,6 +114,7 @@ class ScorePlan:
         return out
 
     # -- pc_sampler / Predictor.update_fn (sampling.py:180-205,450-527) ----------------------------
+    @_device_scoped
     def sde_step(self, x: torch.Tensor, t: float, z: Optional[torch.Tensor] = None, predictor: str = "euler_maruyama",
                  probability_flow: bool = True, beta_min: float = 0.1, beta_max: float = 20.0, n_scales: int = 1000,
                  mode="split3") -> Tuple[torch.Tensor, torch.Tensor]:
@@ -110,6 +129,7 @@ class ScorePlan:
         return x_next, x_mean
 
     # -- the OIL loop (run/opt_main.py:202-220) ------------------------------------------------------
+    @_device_scoped
     def oil_loop(self, x: torch.Tensor, T: torch.Tensor, uv: torch.Tensor, K: torch.Tensor,
                  conf: Optional[torch.Tensor], t_sched: Sequence[float], phase_switch: Optional[int] = None,
                  dump_steps: Iterable[int] = (), beta_min: float = 0.1, beta_max: float = 20.0, n_scales: int = 1000,
@@ -138,6 +158,7 @@ class ScorePlan:
 
 
 # -- gradient_field_gen (simple_zeroshot_opt.py:46-125) ------------------------------------------------
+@_device_scoped
 def grad_field(uv: torch.Tensor, x: torch.Tensor, K: torch.Tensor, conf: Optional[torch.Tensor] = None,
                T: Optional[torch.Tensor] = None, clamp_conf_inplace: bool = True
                ) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -165,6 +186,7 @@ def axes_mask(rot_axes: str) -> int:
 
 
 # -- IPO (run/opt_main.py:175-201) ------------------------------------------------------------------------
+@_device_scoped
 def ipo_fit(x0: torch.Tensor, uv: torch.Tensor, K: torch.Tensor, keylist: Sequence[int], rot_axes: str, ipo_T: float,
             minT: float, maxT: float, iters: int = 500, b_global: Optional[int] = None, lr: float = 0.1,
             pelvis: Tuple[int, int] = (0, 0), ray_init: bool = False):
@@ -185,6 +207,7 @@ def ipo_fit(x0: torch.Tensor, uv: torch.Tensor, K: torch.Tensor, keylist: Sequen
     return R, T, x_rot, qs
 
 
+@_device_scoped
 def rotopt_forward(q, scale, xk, T0, K, minT, maxT):
     q, scale, xk, T0, K = (_f32(t, n) for t, n in ((q, "q"), (scale, "scale"), (xk, "xk"), (T0, "T0"), (K, "K")))
     B, nk = xk.shape[0], xk.shape[1]
@@ -194,6 +217,7 @@ def rotopt_forward(q, scale, xk, T0, K, minT, maxT):
     return out
 
 
+@_device_scoped
 def rotopt_backward(q, scale, xk, T0, K, minT, maxT, d_uv):
     q, scale, xk, T0, K, d_uv = (_f32(t, n) for t, n in ((q, "q"), (scale, "scale"), (xk, "xk"), (T0, "T0"),
                                                          (K, "K"), (d_uv, "d_uv")))
@@ -207,6 +231,7 @@ def rotopt_backward(q, scale, xk, T0, K, minT, maxT, d_uv):
 
 
 # -- eval_multi + procrustes (h36m.py:365-442, transforms.py:42-148) ------------------------------------------
+@_device_scoped
 def eval_multi(pred: torch.Tensor, gt: torch.Tensor, protocol2: bool = False,
                joint_subset: Optional[Sequence[int]] = None, return_all: bool = False, return_aligned: bool = False):
     """pred [N,S,J,3] float32, gt [N,J,3] (converted to float64).  Returns
@@ -232,6 +257,7 @@ def eval_multi(pred: torch.Tensor, gt: torch.Tensor, protocol2: bool = False,
     return out
 
 
+@_device_scoped
 def pck_auc(pred: torch.Tensor, gt: torch.Tensor, select: Optional[torch.Tensor] = None,
             joint_subset: Optional[Sequence[int]] = None) -> Tuple[float, float]:
     """(PCK@150mm, AUC) of MPI-INF-3DHP (utils.py:814-849) for the hypothesis ``select[n]`` of every pose
@@ -250,6 +276,7 @@ def pck_auc(pred: torch.Tensor, gt: torch.Tensor, select: Optional[torch.Tensor]
     return float(pcks[30]), float(pcks.mean())
 
 
+@_device_scoped
 def hypothesis_std(pred: torch.Tensor) -> Tuple[float, float, float]:
     """Diversity of the hypotheses as lib/dataset/mpii3dHP.py:487-490 reports it: per coordinate, the
     std over the S hypotheses of the root-relative joints 1..J-1, averaged over poses and joints.
@@ -280,6 +307,7 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 # -- the whole per-hypothesis pipeline (run/opt_main.py:166-222) ------------------------------------------
+@_device_scoped
 def run_pose_optimisation(plan: ScorePlan, db_2d: torch.Tensor, K: torch.Tensor, clusters: torch.Tensor, cfg: dict,
                           hypo: int = 1, mode="split3", t_start: float = 0.1, b_global: Optional[int] = None,
                           steps: Optional[int] = None, phase_switch: Optional[int] = None,
