@@ -142,7 +142,7 @@ def test_rotopt_adam_loop_through_the_mirror(lib, golden):
             loss = torch.mean(criterion(rot2d[:, :, :2], condition[:, kl, :2]))
             loss.backward()
             opt.step()
-            assert abs(float(loss) - g[f"{tag}_loss"][i]) / g[f"{tag}_loss"][i] < 1e-4
+            assert abs(float(loss.detach()) - g[f"{tag}_loss"][i]) / g[f"{tag}_loss"][i] < 1e-4
         q = torch.cat([rot_opt.rot_vect] + [getattr(rot_opt, f"rot_vect_{a}", torch.zeros(16, 1, device=device))
                                             for a in "xyz"], dim=-1).detach().cpu().numpy()
         assert rel_err(q, g[f"{tag}_q_traj"][9]) < 1e-4
