@@ -110,6 +110,7 @@ def load_into(torch, module, W):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true", help="do not write fixtures")
+    ap.add_argument("--only", default="", help="comma-separated fixture names to (re)write; default: all")
     args = ap.parse_args()
     R = _import_reference()
     torch = R.torch
@@ -420,6 +421,61 @@ def main():
              abs(mp_ref.mean() - mp_or.mean()), 1e-4 * max(1.0, mp_ref.mean()))
     out["oil_small"] = dict(x_final=results, T_final=Tt.numpy(), post_scale=np.float32(0.05), mpjpe=mp_ref)
 
+    # ---- 7c. BASELINE configs[0] size: 1,024 poses through the reference's IPO (500 Adam iterations) and its
+    # 1000-step OIL loop (damped network, realistic pose scale).  The aggregate MPJPE over 1,024 poses is the
+    # quantity north_star bounds by 0.1 mm; per-pose values carry the float32 noise floor discussed above.
+    print("C1 size: 1024 poses, reference IPO + OIL loop (1000 steps) -- takes a few minutes")
+    N1, seed1 = 1024, 2024
+    ds1 = zo.make_synthetic_dataset(N1, seed=seed1, n_clusters=1)
+    uv1, K1n = ds1["db_2d"].copy(), ds1["camera_param"].copy()
+    zcfg = zo.H36M_ZEDO_CFG
+    x01 = zo.init_hypothesis(ds1["clusters"], 0, N1)
+    uv1_t, K1_t = torch.tensor(uv1[:, :, :2]), torch.tensor(K1n)
+    pelvis = torch.cat((uv1_t[:, 0, :], torch.ones((N1, 1))), axis=-1)
+    T01 = torch.inverse(K1_t).bmm(pelvis[:, :, None]).permute(0, 2, 1)
+    T01 = T01 / torch.norm(T01, dim=-1, keepdim=True) * zcfg["IPO_T"]
+    rot1 = R.szo.RotOpt(N1, axis=zcfg["RotAxes"], minT=zcfg["IPO_minScaleT"], maxT=zcfg["IPO_maxScaleT"])
+    opt1 = torch.optim.Adam(rot1.parameters(), lr=0.1)
+    crit1 = torch.nn.L1Loss(reduction="none")
+    kl1 = zcfg["IPO_keylist"]
+    xk1 = torch.tensor(x01)[:, kl1, :]
+    for it in range(zcfg["IPO_iterations"]):
+        opt1.zero_grad()
+        rot2d = rot1(xk1, T01, K1_t)
+        loss = torch.mean(crit1(rot2d[:, :, :2], uv1_t[:, kl1, :2]))
+        loss.backward()
+        opt1.step()
+    R1 = rot1.generate_matrix().detach().numpy()
+    T1 = (T01 * torch.clamp(rot1.scale, min=zcfg["IPO_minScaleT"], max=zcfg["IPO_maxScaleT"])).detach().numpy()
+    sampling_fn1 = R.sampling.get_sampling_fn(cfg, sde, (N1, 17, 3), lambda x: x, 0.01, device="cpu")
+    conf1_t = torch.tensor(uv1[:, :, 2].copy())
+    with torch.no_grad():
+        dx = torch.tensor(R1).bmm(torch.tensor(x01).permute(0, 2, 1)).permute(0, 2, 1).contiguous()
+        Tt1 = torch.tensor(T1)
+        for i in range(n_steps):
+            if i < n_steps // 5:
+                jg = R.szo.gradient_field_gen(uv1_t, dx, K1_t, t=Tt1, conf=conf1_t, returnT=False)
+            else:
+                jg, Tt1 = R.szo.gradient_field_gen(uv1_t, dx, K1_t, conf=conf1_t, returnT=True)
+            dx += jg
+            _, res1 = sampling_fn1(model_s, condition=uv1_t * 0, gradient=jg, denoise_x=dx, t=ts[i], t_step=i,
+                                   args=None)
+            dx = torch.tensor(res1)
+    gt1 = ds1["db_3d"].astype(np.float64)
+    mp1_ref = np.array([zo.mpjpe(res1[n], gt1[n]) for n in range(N1)])
+    x_rot1 = np.einsum("bij,bnj->bni", R1, x01).astype(np.float32)
+    xs1, _, _ = zo.oil_loop(Ws, x_rot1, T1, uv1[:, :, :2], K1n, uv1[:, :, 2].copy())
+    mp1_or = np.array([zo.mpjpe(xs1[n], gt1[n]) for n in range(N1)])
+    print(f"      (info) C1 MPJPE level {mp1_ref.mean():.4f} m; per-pose |dMPJPE| mean "
+          f"{np.abs(mp1_ref - mp1_or).mean() * 1e3:.3f} mm, max {np.abs(mp1_ref - mp1_or).max() * 1e3:.3f} mm; "
+          f"aggregate {abs(mp1_ref.mean() - mp1_or.mean()) * 1e3:.4f} mm")
+    ck.bound("C1 (1024 poses) aggregate |dMPJPE| in metres (north_star: 0.1 mm)", abs(mp1_ref.mean() - mp1_or.mean()),
+             1e-4)
+    ck.bound("C1 (1024 poses) per-pose |dMPJPE| mean in metres (float32 noise floor, tol 1 mm)",
+             np.abs(mp1_ref - mp1_or).mean(), 1e-3)
+    out["c1"] = dict(seed=np.int64(seed1), R=R1, T=T1, x_final=res1, T_final=Tt1.numpy(), mpjpe=mp1_ref,
+                     post_scale=np.float32(0.05))
+
     # ---- 8. Procrustes and eval_multi ---------------------------------------------------------------
     print("procrustes / eval_multi")
     rng = np.random.default_rng(11)
@@ -483,7 +539,10 @@ def main():
     print(f"oracle matches the reference on {len(ck.rows)} checks")
     if not args.check:
         os.makedirs(GOLD, exist_ok=True)
+        only = {n for n in args.only.split(",") if n}
         for name, d in out.items():
+            if only and name not in only:
+                continue
             path = os.path.join(GOLD, f"{name}.npz")
             np.savez_compressed(path, **d)
             print(f"wrote {os.path.relpath(path, ROOT)} ({os.path.getsize(path) / 1024:.0f} KiB)")
