@@ -107,9 +107,50 @@ def load_into(torch, module, W):
     return module
 
 
+def pin_formats(R, ck, out):
+    # ---- 9. dataset file formats: the reference's own loaders on synthetic files ---------------------------
+    print("dataset formats (H36M pickle items, 3DPW npz) through the reference's loaders")
+    import pickle
+    import tempfile
+    dsf = zo.make_synthetic_dataset(30, seed=31, n_clusters=2)
+    items = zo.h36m_items_from_arrays(dsf)
+    det = {"test": {"joint3d_image": np.concatenate([dsf["db_2d"][:, :, :2] + 1.5, np.zeros((30, 17, 1), np.float32)], -1),
+                    "confidence": dsf["db_2d"][:, :, 2:3].copy()}}
+    fm = {}
+    with tempfile.TemporaryDirectory() as tmp, redirect_stdout(io.StringIO()):
+        with open(os.path.join(tmp, "h36m_test.pkl"), "wb") as f:
+            pickle.dump(items, f)
+        with open(os.path.join(tmp, "h36m_sh_dt_ft.pkl"), "wb") as f:
+            pickle.dump(det, f)
+        np.savez(os.path.join(tmp, "pw3d_test.npz"), **zo.pw3d_npz_from_arrays(dsf))
+        h_gt = R.H36M(tmp, "test", gt2d=True, abs_coord=True)
+        h_dt = R.H36M(tmp, "test", gt2d=False, abs_coord=True)
+        pw_ds = R.PW3D(tmp, "test", abs_coord=True)
+        rngf = np.random.default_rng(3)
+        preds_f = (dsf["db_3d"][:, None] + rngf.normal(0, 0.03, (30, 4, 17, 3))).astype(np.float32)
+        fm["h36m_eval_p1"] = np.float64(h_gt.eval_multi(preds_f, protocol2=False))
+        fm["h36m_eval_p2"] = np.float64(h_gt.eval_multi(preds_f, protocol2=True))
+        fm["pw3d_eval_p1"] = np.float64(pw_ds.eval_multi(preds_f, protocol2=False))
+    ck.check("H36M loader db_3d == absolute synthetic poses (metres)", h_gt.db_3d,
+             (dsf["db_3d"].astype(np.float64) + dsf["root"][:, None, :]).astype(np.float32), 1e-6)
+    ck.check("H36M loader camera_param", h_gt.camera_param, dsf["camera_param"], 0.0)
+    ck.check("PW3D loader db_3d (order_change inverted by the generator)", pw_ds.db_3d, h_gt.db_3d, 1e-6)
+    agg_f, _, _ = zo.eval_multi(preds_f.astype(np.float64), (dsf["db_3d"] - dsf["db_3d"][:, 0:1]).astype(np.float64),
+                                actions=dsf["actions"])
+    ck.check("H36M.eval_multi on the loaded items (action-wise)", agg_f, fm["h36m_eval_p1"], 1e-6)
+    fm.update(h36m_db2d_gt=np.asarray(h_gt.db_2d), h36m_db2d_dt=np.asarray(h_dt.db_2d), h36m_db3d=h_gt.db_3d,
+              h36m_K=h_gt.camera_param, pw3d_db2d=pw_ds.db_2d, pw3d_db3d=pw_ds.db_3d, pw3d_K=pw_ds.camera_param,
+              preds=preds_f, det_xy=det["test"]["joint3d_image"], det_conf=det["test"]["confidence"],
+              seed=np.int64(31))
+    out["formats"] = fm
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true", help="do not write fixtures")
+    ap.add_argument("--formats-only", action="store_true",
+                    help="run only the dataset-format section and write formats.npz (PINNING.txt is left alone)")
     ap.add_argument("--only", default="", help="comma-separated fixture names to (re)write; default: all")
     args = ap.parse_args()
     R = _import_reference()
@@ -118,6 +159,14 @@ def main():
     torch.set_num_threads(os.cpu_count() or 1)
     ck = Checker()
     out = {}
+    if args.formats_only:
+        pin_formats(R, ck, out)
+        if not ck.all_ok():
+            raise SystemExit("oracle does NOT match the reference")
+        if not args.check:
+            np.savez_compressed(os.path.join(GOLD, "formats.npz"), **out["formats"])
+            print("wrote tests/golden/formats.npz")
+        return
 
     # ---- 1. SDE scalars and the time grid ---------------------------------------------------
     print("sde / time grid")
@@ -532,6 +581,8 @@ def main():
     ck.check("PW3D.eval_multi(protocol2=True) plain mean", agg_pw, e_pw, 1e-12)
     ev["agg_pw3d_p1"] = np.float64(e_pw)
     out["eval"] = dict(preds=preds, gts=gts, actions=actions, aligned=al_ref.astype(np.float64), **ev)
+
+    pin_formats(R, ck, out)
 
     print()
     if not ck.all_ok():

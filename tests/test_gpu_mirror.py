@@ -202,6 +202,28 @@ def test_dataset_eval_variants(lib, golden):
     assert np.allclose(hp.last_std, zo.hypothesis_std(preds), rtol=1e-4)  # the reference's float32 arithmetic
 
 
+def test_dataset_formats_against_the_reference_loaders(lib, golden):
+    """ArrayPoseDataset.from_h36m_items / from_pw3d_npz build the arrays the reference's own loaders built from the
+    same synthetic files (tests/golden/formats.npz), and eval_multi on them gives the reference's numbers."""
+    from lib.dataset.synthetic import ArrayPoseDataset
+    g = golden("formats")
+    ds = zo.make_synthetic_dataset(30, seed=int(g["seed"]), n_clusters=2)
+    items = zo.h36m_items_from_arrays(ds)
+    h = ArrayPoseDataset.from_h36m_items(items, gt2d=True, abs_coord=True)
+    assert np.array_equal(h.db_3d, g["h36m_db3d"]) and np.array_equal(h.camera_param, g["h36m_K"])
+    assert np.array_equal(h.db_2d, g["h36m_db2d_gt"].astype(np.float32))
+    hd = ArrayPoseDataset.from_h36m_items(items, gt2d=False, detections=(g["det_xy"], g["det_conf"]))
+    assert np.array_equal(hd.db_2d, g["h36m_db2d_dt"])
+    with pytest.raises(ValueError):
+        ArrayPoseDataset.from_h36m_items(items, gt2d=False)
+    assert abs(h.eval_multi(g["preds"], protocol2=False) - float(g["h36m_eval_p1"])) < 2e-7
+    assert abs(h.eval_multi(g["preds"], protocol2=True) - float(g["h36m_eval_p2"])) < 2e-7
+    pw = ArrayPoseDataset.from_pw3d_npz(zo.pw3d_npz_from_arrays(ds), abs_coord=True)
+    assert np.array_equal(pw.db_3d, g["pw3d_db3d"]) and np.array_equal(pw.camera_param, g["pw3d_K"])
+    assert np.abs(pw.db_2d - g["pw3d_db2d"]).max() < 1e-3  # pixels; einsum vs per-pose dot
+    assert abs(pw.eval_multi(g["preds"], protocol2=False) - float(g["pw3d_eval_p1"])) < 2e-7
+
+
 def test_control_model_through_the_mirror(lib, golden):
     from lib.algorithms.advanced.control_model import Control_ScoreModelFC_Adv
     from lib.algorithms.advanced import utils as mutils, sde_lib

@@ -38,6 +38,23 @@ def test_schedule_and_synthetic_generators_match_oracle(zr, golden):
     assert sy.H36M_ZEDO_CFG == zo.H36M_ZEDO_CFG and zr.axes_mask("xyz") == 7 and zr.axes_mask("z") == 4
 
 
+def test_dataset_format_generators_match_oracle(zr):
+    """The H36M pickle-item and 3DPW npz generators of the package equal the oracle's copies (the golden vectors of
+    tests/golden/formats.npz were produced by the reference's loaders from the oracle's)."""
+    from zedo_release_b200 import synthetic as sy
+    ds = zo.make_synthetic_dataset(9, seed=31, n_clusters=2)
+    a, b = zo.h36m_items_from_arrays(ds), sy.h36m_items_from_arrays(ds)
+    for ia, ib in zip(a, b):
+        assert ia["action"] == ib["action"] and ia["image_path"] == ib["image_path"]
+        assert np.array_equal(ia["joint_3d_camera"], ib["joint_3d_camera"])
+        assert np.array_equal(ia["joint_3d_image"], ib["joint_3d_image"])
+        assert all(ia["camera_param"][k] == ib["camera_param"][k] for k in ("fx", "fy", "cx", "cy"))
+    pa, pb = zo.pw3d_npz_from_arrays(ds), sy.pw3d_npz_from_arrays(ds)
+    assert np.array_equal(pa["keypoints3d17_relative"], pb["keypoints3d17_relative"])
+    assert np.array_equal(pa["root_cam"], pb["root_cam"])
+    assert np.array_equal(pa["cam_param"].item()["f"], pb["cam_param"].item()["f"])
+
+
 def test_aggregate_errors(zr):
     e = np.arange(30, dtype=np.float64)
     acts = 2 + np.arange(30) % 15

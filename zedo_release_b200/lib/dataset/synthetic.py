@@ -21,11 +21,68 @@ class ArrayPoseDataset:
         self.joint_subset = joint_subset
         self.name = name
         self.last_index = None  # argmin over hypotheses of the last eval_multi call
+        self.gt_eval = None     # root-relative metres in the source's own dtype, when built from dataset items
+        self.image_name = None
 
     @classmethod
     def synthetic_h36m(cls, n_poses, seed=1234, detected_2d=True):
         ds = _syn.make_synthetic_dataset(n_poses, n_joints=17, seed=seed, detected_2d=detected_2d)
         return cls(ds["db_3d"], ds["db_2d"], ds["camera_param"], actions=ds["actions"], name="h36m-synthetic")
+
+    @classmethod
+    def from_h36m_items(cls, items, gt2d=True, detections=None, abs_coord=True, name="h36m"):
+        """From the ground-truth items of ``h36m_<subset>.pkl`` (the in-memory format of
+        lib/dataset/h36m.py:205-263; reading the pickle is the caller's business): ``db_3d`` =
+        joint_3d_camera / 1000 (float32, root-relative unless ``abs_coord``), ``camera_param`` from
+        fx, fy, cx, cy, ``db_2d`` = joint_3d_image[..., :2] + confidence 1 (``gt2d``) or
+        ``detections`` = (joint3d_image [N,17,>=2], confidence [N,17,1]) of ``h36m_sh_dt_ft.pkl``.
+        ``eval_multi`` scores against the items' own joint_3d_camera in its stored dtype
+        (h36m.py:402-403), action-wise."""
+        labels = np.array([it["joint_3d_camera"] for it in items], dtype=np.float32)
+        image = np.array([it["joint_3d_image"] for it in items], dtype=np.float32)
+        K = np.zeros((len(items), 3, 3), np.float32)
+        for n, it in enumerate(items):
+            cp = it["camera_param"]
+            K[n, 0, 0], K[n, 1, 1] = np.asarray(cp["fx"]).item(), np.asarray(cp["fy"]).item()
+            K[n, 0, 2], K[n, 1, 2], K[n, 2, 2] = np.asarray(cp["cx"]).item(), np.asarray(cp["cy"]).item(), 1
+        if not abs_coord:
+            labels = labels - labels[:, 0:1]
+        labels = labels / 1000.0
+        if gt2d:
+            d2 = np.concatenate((image[..., :2], np.ones((len(items), image.shape[1], 1))), axis=-1)
+        else:
+            if detections is None:
+                raise ValueError("gt2d=False needs detections=(joint3d_image, confidence)")
+            d2 = np.concatenate((np.asarray(detections[0])[:, :, :2], np.asarray(detections[1])), axis=-1)
+        ds = cls(labels, d2, K, actions=[it["action"] for it in items], name=name)
+        gt = np.array([it["joint_3d_camera"] for it in items])
+        ds.gt_eval = (gt - gt[:, 0:1]) / 1000.0
+        ds.image_name = [it.get("image_path") for it in items]
+        return ds
+
+    @classmethod
+    def from_pw3d_npz(cls, data, abs_coord=True, name="3dpw"):
+        """From the arrays of ``pw3d_<subset>.npz`` (lib/dataset/pw3d.py:177-227): joints re-ordered to the
+        H36M topology (``order_change``), absolute = relative + root_cam, K from cam_param f / c, ``db_2d`` =
+        the projection (K X) / z whose third column, 1, serves as the confidence."""
+        cam = data["cam_param"].item() if hasattr(data["cam_param"], "item") else data["cam_param"]
+        rel, root = np.asarray(data["keypoints3d17_relative"]), np.asarray(data["root_cam"])
+        N = len(rel)
+        X = np.empty((N, 17, 3), np.float64)
+        absx = rel[:, :, :3] + root[:, None, :]
+        for i in range(17):
+            X[:, _syn.PW3D_ORDER[i]] = absx[:, i]
+        K = np.zeros((N, 3, 3), np.float64)
+        K[:, 0, 0], K[:, 1, 1] = cam["f"][:, 0], cam["f"][:, 1]
+        K[:, 0, 2], K[:, 1, 2], K[:, 2, 2] = cam["c"][:, 0], cam["c"][:, 1], 1
+        proj = np.einsum("bij,bnj->bni", K, X)
+        d2 = proj / proj[:, :, 2:]
+        labels = X.astype(np.float32)
+        if not abs_coord:
+            labels = labels - labels[:, 0:1]
+        ds = cls(labels, d2.astype(np.float32), K.astype(np.float32), name=name)
+        ds.image_name = list(data["image_path"]) if "image_path" in data else None
+        return ds
 
     def __len__(self):
         return len(self.db_3d)
@@ -43,7 +100,7 @@ class ArrayPoseDataset:
         With ``name='3dhp'`` the 3DHP extras (mpii3dHP.py:480-490) are computed too: ``last_pck``,
         ``last_auc`` on the selected hypotheses and ``last_std`` (diversity)."""
         assert len(preds) == len(self.db_3d)
-        gt = self.db_3d - self.db_3d[:, 0:1]
+        gt = self.gt_eval if self.gt_eval is not None else self.db_3d - self.db_3d[:, 0:1]
         actions = self.actions
         if sample_interval is not None:
             preds = preds[::sample_interval]

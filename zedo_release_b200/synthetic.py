@@ -126,6 +126,40 @@ def make_synthetic_dataset(n_poses, n_joints=17, seed=1234, detected_2d=True, n_
     )
 
 
+PW3D_ORDER = [5, 2, 6, 3, 11, 14, 12, 15, 13, 16, 1, 4, 8, 10, 0, 7, 9]  # lib/dataset/pw3d.py:76
+
+
+def h36m_items_from_arrays(ds, dtype=np.float64):
+    """The synthetic dataset as the list of ground-truth items ``h36m_<subset>.pkl`` holds
+    (lib/dataset/h36m.py:205-234): ``joint_3d_camera`` [17,3] millimetres (absolute), ``joint_3d_image``
+    [17,3] (u, v, depth), ``camera_param`` {fx, fy, cx, cy} as 0-d arrays, ``image_path``, ``action``."""
+    items = []
+    cam_mm = (ds["db_3d"].astype(np.float64) + ds["root"].astype(np.float64)[:, None, :]) * 1000.0
+    for n in range(len(cam_mm)):
+        K = ds["camera_param"][n]
+        img = np.concatenate([ds["db_2d"][n, :, :2], cam_mm[n, :, 2:3]], axis=-1)
+        items.append({"joint_3d_camera": cam_mm[n].astype(dtype), "joint_3d_image": img.astype(dtype),
+                      "camera_param": {"fx": np.array(K[0, 0]), "fy": np.array(K[1, 1]), "cx": np.array(K[0, 2]),
+                                       "cy": np.array(K[1, 2])},
+                      "image_path": f"synthetic/{n:08d}.jpg", "action": int(ds["actions"][n])})
+    return items
+
+
+def pw3d_npz_from_arrays(ds):
+    """The synthetic dataset under the keys of ``pw3d_<subset>.npz`` (lib/dataset/pw3d.py:184-199): joints in the
+    file's own order (``order_change`` maps file joint i to H36M joint PW3D_ORDER[i]), root-relative + ``root_cam``."""
+    N = len(ds["db_3d"])
+    rel = np.empty((N, 17, 3), np.float64)
+    for i in range(17):
+        rel[:, i] = ds["db_3d"][:, PW3D_ORDER[i]]
+    K = ds["camera_param"].astype(np.float64)
+    return {"keypoints3d17_relative": rel, "root_cam": ds["root"].astype(np.float64),
+            "cam_param": np.array({"f": np.stack([K[:, 0, 0], K[:, 1, 1]], -1), "c": np.stack([K[:, 0, 2], K[:, 1, 2]], -1)},
+                                  dtype=object),
+            "image_width": np.full(N, 1920), "image_height": np.full(N, 1080),
+            "image_path": np.array([f"synthetic/{n:08d}.jpg" for n in range(N)])}
+
+
 H36M_ZEDO_CFG = dict(IPO_iterations=500, IPO_keylist=[0, 1, 4], RotAxes="z", IPO_T=3,
                      IPO_minScaleT=0.5, IPO_maxScaleT=2, OIL_iterations=1000,
                      sampling_eps=0.01)  # configs/optim/concat_pose_optimization_h36m.py:70-81
