@@ -258,6 +258,31 @@ def main():
         net[f"out_{t}"] = ref
     out["net"] = dict(x=xb, weights_seed=np.int64(0), **net)
 
+    # 'fourier' time embedding (configs/default_pose_gen_configs.py:71; model.py:246-250): same weights + gauss_proj.W.
+    # The Fourier features multiply log(t) by N(0, 30^2) frequencies, so one ulp of log(t) moves the features by 2e-4;
+    # zo.log_f32 is the correctly rounded float32 logarithm, which is what torch.log returns on the whole time grid.
+    cfg_f = ref_config()
+    cfg_f.model.embedding_type = "fourier"
+    Wf = zo.make_weights(seed=0, fourier=True)
+    model_f = load_into(torch, R.ScoreModelFC_Adv(cfg_f, n_joints=17, joint_dim=3, hidden_dim=1024,
+                                                  embed_dim=512, cond_dim=3), Wf)
+    netf = {}
+    for t in (0.1, 0.05, 0.01):
+        lab = torch.ones(8) * torch.tensor(t) * 999
+        with torch.no_grad():
+            ref = model_f(torch.tensor(xb), lab, torch.zeros(8, 17, 2), None).numpy()
+            emb_ref = model_f.gauss_proj(torch.log(lab[:1])).numpy()
+        t999 = np.float32(t) * np.float32(999)
+        ck.check(f"fourier embedding t={t}", zo.gaussian_fourier_projection(zo.log_f32(t999), Wf["gauss_proj.W"]),
+                 emb_ref, 2e-6)
+        ck.check(f"score forward (fourier embedding) t={t}", zo.score_forward(Wf, xb, t999), ref, 2e-5)
+        netf[f"out_{t}"] = ref
+        netf[f"emb_{t}"] = emb_ref
+    grid = zo.oil_time_grid() * np.float32(999)
+    ck.check("log_f32 == torch.log on the OIL time grid (bit-exact)", zo.log_f32(grid), torch.log(torch.tensor(grid)).numpy(),
+             0.0)
+    out["net_fourier"] = dict(x=xb, weights_seed=np.int64(0), **netf)
+
     # J=12 variant (SyRIP) and the control network (opt_main_infant.py:122-148)
     W12 = zo.make_weights(seed=2, n_joints=12)
     m12 = load_into(torch, R.ScoreModelFC_Adv(cfg, n_joints=12, joint_dim=3, hidden_dim=1024,

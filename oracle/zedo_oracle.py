@@ -133,9 +133,30 @@ def linear(x, w, b):
     return (x @ w.T + b[None, :]).astype(f32)
 
 
+def log_f32(t) -> np.ndarray:
+    """``torch.log`` of a float32 tensor (model.py:249).  torch's float32 logarithm is correctly rounded on the whole
+    OIL time grid (checked against the imported reference by gen_golden.py) while numpy's float32 SIMD log is 1 ulp
+    off on 46 of the 1000 grid points -- and the Fourier features turn 1 ulp of log t into 2e-4 -- so the logarithm
+    is formed in float64 and rounded once."""
+    return np.log(np.atleast_1d(np.asarray(t, dtype=f32)).astype(np.float64)).astype(f32)
+
+
+def gaussian_fourier_projection(x, Wp) -> np.ndarray:
+    """``GaussianFourierProjection.forward`` (model.py:27-36): x_proj = ((x * W) * 2) * pi in float32 (the python
+    scalars are cast to the tensor dtype), [sin, cos]."""
+    x = np.atleast_1d(np.asarray(x, dtype=f32))
+    proj = ((x[:, None] * np.asarray(Wp, dtype=f32)[None, :]) * f32(2.0)) * f32(np.pi)
+    return np.concatenate([np.sin(proj, dtype=f32), np.cos(proj, dtype=f32)], axis=1).astype(f32)
+
+
 def time_embed(W: Weights, t999) -> np.ndarray:
-    """temb = SiLU(shared_time_embed(posit_proj(t))) (model.py:253-259); [n_t, embed_dim]."""
-    emb = timestep_embedding(t999, W["shared_time_embed.0.weight"].shape[1])
+    """temb = SiLU(shared_time_embed(emb)) (model.py:246-259); [n_t, embed_dim].  emb = posit_proj(t) for the
+    'positional' embedding of every shipped optimisation config, gauss_proj(log t) for 'fourier' (the default of
+    configs/default_pose_gen_configs.py:71), which is recognised by its state_dict entry ``gauss_proj.W``."""
+    if "gauss_proj.W" in W:
+        emb = gaussian_fourier_projection(log_f32(t999), W["gauss_proj.W"])
+    else:
+        emb = timestep_embedding(t999, W["shared_time_embed.0.weight"].shape[1])
     return silu(linear(emb, W["shared_time_embed.0.weight"], W["shared_time_embed.0.bias"]))
 
 
@@ -676,7 +697,7 @@ def skeleton_template(n_joints=17):
     return t
 
 
-def make_weights(seed=0, n_joints=17, hidden=1024, embed=512, n_blocks=2, control=False) -> Weights:
+def make_weights(seed=0, n_joints=17, hidden=1024, embed=512, n_blocks=2, control=False, fourier=False) -> Weights:
     """Random-init weights with the reference's state_dict names and the default
     ``nn.Linear`` init range U(-1/sqrt(fan_in), 1/sqrt(fan_in)); GroupNorm affine is
     randomised (U(0.5,1.5), U(-0.2,0.2)) so the affine path is exercised.  Generated with
@@ -722,6 +743,8 @@ def make_weights(seed=0, n_joints=17, hidden=1024, embed=512, n_blocks=2, contro
             lin(f"b{k}_dense2_copy", hidden, hidden)
             lin(f"b{k}_dense2_t_copy", embed, hidden)
             gn(f"b{k}_gnorm2_copy")
+    if fourier:  # GaussianFourierProjection(embed_dim, scale=30): W ~ N(0, 30^2), drawn last so the other tensors
+        W["gauss_proj.W"] = (rng.normal(0, 1, (embed // 2,)) * 30.0).astype(f32)  # match the positional variant
     return W
 
 

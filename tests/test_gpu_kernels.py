@@ -130,6 +130,34 @@ def test_score_forward_golden(zr, golden, plan17, mode, tol):
         assert rel_err(out.cpu().numpy(), g[f"out_{t}"]) < tol, (mode, t)
 
 
+@pytest.mark.parametrize("mode", ["fp32", "split3"])
+def test_score_forward_fourier_embedding_golden(zr, golden, mode):
+    """A state dict that carries gauss_proj.W selects the 'fourier' time embedding (model.py:27-36,246-250):
+    forward against the reference's outputs, and a 30-step OIL loop (bias table built from log t) against the oracle."""
+    g = golden("net_fourier")
+    W = zo.make_weights(seed=int(g["weights_seed"]), fourier=True)
+    p = zr.ScorePlan(W, n_joints=17, max_batch=256, device=0)
+    for t in (0.1, 0.05, 0.01):
+        out = p.forward(dev(g["x"]), float(np.float32(t) * np.float32(999)), mode=mode)
+        assert rel_err(out.cpu().numpy(), g[f"out_{t}"]) < 2e-5, (mode, t)
+    B = 200
+    ds = zo.make_synthetic_dataset(B, seed=9, n_clusters=1)
+    uv, K, conf = ds["db_2d"][:, :, :2], ds["camera_param"], ds["db_2d"][:, :, 2]
+    x0 = (ds["db_3d"] + 0.05).astype(np.float32)
+    T0 = zo.init_translation(uv, K, 3.0).reshape(B, 3)
+    ts = zo.oil_time_grid()[185:215]
+    xg, Tg = dev(x0), dev(T0)
+    p.oil_loop(xg, Tg, dev(uv), dev(K), dev(conf), ts, phase_switch=15, mode=mode)
+    p.close()
+    xo, To, _ = zo.oil_loop_schedule(W, x0, T0.reshape(B, 1, 3), uv, K, conf.copy(), ts, 15)
+    assert rel_err(xg.cpu().numpy(), xo) < 2e-4 and rel_err(Tg.cpu().numpy(), To.reshape(B, 3)) < 2e-4
+    # a gauss_proj.W of the wrong size is a shape error, not a silent fall-back to the positional embedding
+    bad = dict(W)
+    bad["gauss_proj.W"] = W["gauss_proj.W"][:100]
+    with pytest.raises(Exception):
+        zr.ScorePlan(bad, n_joints=17, max_batch=64, device=0)
+
+
 @pytest.mark.parametrize("B", [1, 127, 128, 129, 300, 4096])
 def test_score_forward_vs_oracle_ragged_batches(zr, plan17, B):
     W = zo.make_weights(seed=0)

@@ -245,6 +245,34 @@ def test_control_model_through_the_mirror(lib, golden):
     assert rel_err(score.cpu().numpy(), ref) < 1e-4
 
 
+def test_fourier_embedding_through_the_mirror(lib, golden):
+    """embedding_type = 'fourier' (configs/default_pose_gen_configs.py:71): same state_dict keys as the reference
+    (gauss_proj.W), forward against the reference's outputs, scale_by_sigma divides by t (model.py:248,294-296)."""
+    from lib.algorithms.advanced.model import ScoreModelFC_Adv
+    g = golden("net_fourier")
+    cfg = ref_config()
+    cfg.model.embedding_type = "fourier"
+    W = zo.make_weights(seed=int(g["weights_seed"]), fourier=True)
+    m = ScoreModelFC_Adv(cfg, n_joints=17, joint_dim=3, hidden_dim=1024, embed_dim=512, cond_dim=3)
+    assert set(m.state_dict().keys()) == set(W.keys()) | {"sigmas"}
+    sd = {k: torch.tensor(v) for k, v in W.items()}
+    sd["sigmas"] = m.sigmas.clone()
+    m.load_state_dict(sd)
+    m.to(torch.device("cuda")).eval()
+    x = torch.tensor(g["x"], device="cuda")
+    for t in (0.1, 0.05, 0.01):
+        lab = torch.ones(8, device="cuda") * torch.tensor(t) * 999
+        out = m(x, lab, torch.zeros(8, 17, 2, device="cuda"), None)
+        assert rel_err(out.cpu().numpy(), g[f"out_{t}"]) < 2e-5
+        emb = m.gauss_proj(torch.log(lab[:1])).cpu().numpy()
+        assert rel_err(emb, g[f"emb_{t}"]) < 3e-4  # torch's CUDA logf / sinf, 1 ulp of log t = 2e-4 here
+    cfg.model.scale_by_sigma = True
+    lab = torch.ones(8, device="cuda") * 49.95
+    out = m(x, lab, None, None)
+    assert rel_err(out.cpu().numpy(), g["out_0.05"] / np.float32(49.95)) < 2e-5
+    cfg.model.scale_by_sigma = False
+
+
 def test_checkpoint_file_in_the_reference_format(lib, golden, tmp_path):
     """run/opt_main.py:120-137 verbatim: torch.load -> strip `module.` -> model.load_state_dict ->
     ema.load_state_dict -> state['step']; the file is written the way the reference's trainer saves it

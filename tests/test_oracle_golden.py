@@ -66,6 +66,18 @@ def test_score_network(golden):
     assert rel_err(zo.score_forward(W12, g12["x"], g12["t999"]), g12["out"]) < 2e-5
 
 
+def test_score_network_fourier_embedding(golden):
+    """'fourier' time embedding (model.py:27-36,246-250; the default of configs/default_pose_gen_configs.py:71)."""
+    g = golden("net_fourier")
+    W = zo.make_weights(seed=int(g["weights_seed"]), fourier=True)
+    Wp = zo.make_weights(seed=int(g["weights_seed"]))
+    assert all(np.array_equal(W[k], Wp[k]) for k in Wp) and W["gauss_proj.W"].shape == (256,)
+    for t in (0.1, 0.05, 0.01):
+        t999 = np.float32(t) * np.float32(999)
+        assert rel_err(zo.gaussian_fourier_projection(zo.log_f32(t999), W["gauss_proj.W"]), g[f"emb_{t}"]) < 2e-6
+        assert rel_err(zo.score_forward(W, g["x"], t999), g[f"out_{t}"]) < 2e-5
+
+
 def test_control_network(golden):
     g = golden("control")
     W = zo.make_weights(seed=int(g["weights_seed"]), control=True)

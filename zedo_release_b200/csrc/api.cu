@@ -109,7 +109,8 @@ struct zedo_plan {
   float* bs = nullptr;      // [E]
   float* Wt_cat = nullptr;  // [L*H, E]: the `*_t` projections, concatenated
   float* bt_cat = nullptr;  // [L*H]: b_t + b of the matching dense layer
-  float* freqs = nullptr;   // [E/2]
+  float* freqs = nullptr;   // [E/2]: positional frequencies, or gauss_proj.W for the 'fourier' embedding
+  bool fourier = false;     // state dict carries gauss_proj.W (model.py:246-250): emb = [sin, cos](2 pi W log t)
   float* gamma = nullptr;   // [n_gn, H]
   float* beta = nullptr;
   float* post_bias = nullptr;  // [64]
@@ -253,8 +254,18 @@ int ensure_tables(zedo_plan* p, int steps) {
 int build_tables(zedo_plan* p, const float* t999_host, int steps, cudaStream_t st) {
   int rc = ensure_tables(p, steps);
   if (rc) return rc;
+  std::vector<float> logt;
+  if (p->fourier) {
+    // torch.log(used_sigmas) (model.py:249): the float32 logarithm, formed here as the correctly rounded one.  The
+    // features multiply it by N(0, 30^2) frequencies, so the last bit of log t is worth 1e-4 in the features --
+    // the reference's own CPU and GPU libms disagree at that level.
+    logt.resize((size_t)steps);
+    for (int i = 0; i < steps; ++i) logt[i] = (float)std::log((double)t999_host[i]);
+    t999_host = logt.data();
+  }
   ZEDO_CUDA_TRY(cudaMemcpyAsync(p->t999_dev, t999_host, (size_t)steps * sizeof(float), cudaMemcpyHostToDevice, st));
-  if ((rc = launch_timestep_embedding(p->t999_dev, p->freqs, p->emb, steps, p->E / 2, st))) return rc;
+  if ((rc = launch_timestep_embedding(p->t999_dev, p->freqs, p->emb, steps, p->E / 2, p->fourier ? 1 : 0, st)))
+    return rc;
   if ((rc = launch_sgemm_tn(p->emb, p->E, p->Ws, p->E, p->bs, p->temb, p->E, steps, p->E, p->E, st))) return rc;
   if ((rc = launch_silu_inplace(p->temb, (int64_t)steps * p->E, st))) return rc;
   if (p->desc.kind != ZEDO_NET_CONTROL)
@@ -661,6 +672,12 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
     std::vector<float> fr(half);
     const float coef = (float)(-(std::log(10000.0) / (double)(half - 1)));
     for (int k = 0; k < half; ++k) fr[k] = expf((float)k * coef);
+    if (const std::vector<float>* gw = tm.get("gauss_proj.W", (size_t)half)) {
+      p->fourier = true;  // GaussianFourierProjection (model.py:27-36): fixed random frequencies from the checkpoint
+      fr = *gw;
+    } else if (tm.t.count("gauss_proj.W")) {
+      PLAN_TRY(ZEDO_E_SHAPE);
+    }
     PLAN_TRY(upload(p, &p->freqs, fr.data(), fr.size()));
   }
   // workspaces

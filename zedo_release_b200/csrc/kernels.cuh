@@ -32,7 +32,7 @@ int launch_sde_update(const float* x, const float* eps, int ld_eps, const float*
                       int probability_flow, float* x_next, float* x_mean, int64_t B, int D, cudaStream_t st);
 int launch_sgemm_tn(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M,
                     int N, int K, cudaStream_t st, int accumulate = 0);
-int launch_timestep_embedding(const float* t999, const float* freqs, float* emb, int n_steps, int half,
+int launch_timestep_embedding(const float* tin, const float* freqs, float* emb, int n_steps, int half, int fourier,
                               cudaStream_t st);
 int launch_silu_inplace(float* v, int64_t n, cudaStream_t st);
 int launch_gn_silu_rows(const float* in, const float* cbias, const float* addend, const float* gamma,

@@ -56,13 +56,16 @@ sgemm_tn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
   }
 }
 
-// sinusoidal embedding of the time labels (model.py:81-95): one row of E = 2*half per step
-__global__ void timestep_embedding_kernel(const float* __restrict__ t999, const float* __restrict__ freqs,
-                                          float* __restrict__ emb, int n_steps, int half) {
+// embedding of the time labels, one row of E = 2*half per step: [sin(arg), cos(arg)] with
+//   positional (model.py:81-95):  arg = t999 * f_k
+//   fourier    (model.py:27-36):  arg = ((log t999 * W_k) * 2) * pi, one float32 rounding per torch op (tin = log t999)
+__global__ void timestep_embedding_kernel(const float* __restrict__ tin, const float* __restrict__ freqs,
+                                          float* __restrict__ emb, int n_steps, int half, int fourier) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_steps * half) return;
   const int s = i / half, k = i % half;
-  const float arg = t999[s] * freqs[k];
+  const float prod = __fmul_rn(tin[s], freqs[k]);
+  const float arg = fourier ? __fmul_rn(__fmul_rn(prod, 2.0f), 3.14159274101257324f) : prod;
   emb[(int64_t)s * 2 * half + k] = sinf(arg);
   emb[(int64_t)s * 2 * half + half + k] = cosf(arg);
 }
@@ -106,10 +109,10 @@ int launch_sgemm_tn(const float* A, int lda, const float* W, int ldw, const floa
   return 0;
 }
 
-int launch_timestep_embedding(const float* t999, const float* freqs, float* emb, int n_steps, int half,
+int launch_timestep_embedding(const float* tin, const float* freqs, float* emb, int n_steps, int half, int fourier,
                               cudaStream_t st) {
   const int n = n_steps * half;
-  timestep_embedding_kernel<<<(n + 255) / 256, 256, 0, st>>>(t999, freqs, emb, n_steps, half);
+  timestep_embedding_kernel<<<(n + 255) / 256, 256, 0, st>>>(tin, freqs, emb, n_steps, half, fourier);
   ZEDO_LAUNCH_CHECK();
   return 0;
 }

@@ -102,8 +102,6 @@ class Control_ScoreModelFC_Adv(nn.Module):
                 getattr(self, dst).bias.copy_(getattr(self, src).bias)
 
     def zedo_plan(self, batch):
-        if self.time_embedding_type != 'positional':
-            raise NotImplementedError("only the 'positional' time embedding of the shipped configs is implemented")
         return self._plans.get(self, batch, self.n_joints, self.hidden_dim, self.embed_dim, self.n_blocks)
 
     def forward(self, batch, t, condition=None, mask=None):
@@ -117,5 +115,6 @@ class Control_ScoreModelFC_Adv(nn.Module):
         res = self.zedo_plan(bs).forward(batch.reshape(bs, self.n_joints, self.joint_dim), float(labels[0]),
                                          mode=self.gemm_mode)
         if self.config.model.scale_by_sigma:
-            res = res / self.sigmas[t.long()].reshape((-1, 1, 1)).to(res.dtype)
+            used_sigmas = t if self.time_embedding_type == 'fourier' else self.sigmas[t.long()]  # control_model.py:295,300
+            res = res / used_sigmas.reshape((-1, 1, 1)).to(res.dtype)
         return res

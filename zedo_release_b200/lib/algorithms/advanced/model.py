@@ -40,11 +40,17 @@ def get_timestep_embedding(timesteps, embedding_dim, max_positions=10000):
 
 
 class GaussianFourierProjection(nn.Module):
-    """Parameter container for 'fourier' embeddings (model.py:27-36); not supported on the kernel path."""
+    """Gaussian random features for encoding time steps (model.py:27-36).  The score modules hand ``W`` to the plan
+    (state_dict entry ``gauss_proj.W``), which evaluates the features on the device; ``forward`` is kept for callers
+    that use the projection on its own."""
 
     def __init__(self, embed_dim, scale=30.):
         super().__init__()
         self.W = nn.Parameter(torch.randn(embed_dim // 2) * scale, requires_grad=False)
+
+    def forward(self, x):
+        x_proj = x[:, None] * self.W[None, :] * 2 * np.pi
+        return torch.cat([torch.sin(x_proj), torch.cos(x_proj)], dim=-1)
 
 
 class _PlanCache:
@@ -110,8 +116,6 @@ class ScoreModelFC_Adv(nn.Module):
 
     def zedo_plan(self, batch):
         """The packed plan for a batch of this size (also used by the fused sampler fast path)."""
-        if self.time_embedding_type != 'positional':
-            raise NotImplementedError("only the 'positional' time embedding of the shipped configs is implemented")
         if self.joint_dim != 3:
             raise NotImplementedError("joint_dim must be 3")
         return self._plans.get(self, batch, self.n_joints, self.hidden_dim, self.embed_dim, self.n_blocks)
@@ -136,6 +140,7 @@ class ScoreModelFC_Adv(nn.Module):
                 sel = (tt == lab).nonzero(as_tuple=True)[0]
                 res[sel] = plan.forward(x[sel].contiguous(), float(lab), mode=self.gemm_mode)
         if self.config.model.scale_by_sigma:
-            used_sigmas = self.sigmas[t.long()].reshape((-1, 1, 1)).to(res.dtype)
-            res = res / used_sigmas
+            # used_sigmas = t for the 'fourier' embedding, sigmas[t.long()] for 'positional' (model.py:248,253)
+            used_sigmas = t if self.time_embedding_type == 'fourier' else self.sigmas[t.long()]
+            res = res / used_sigmas.reshape((-1, 1, 1)).to(res.dtype)
         return res
