@@ -333,7 +333,7 @@ def main():
     ap.add_argument("--poses", type=int, default=262144, help="poses per GPU (BASELINE configs[1])")
     ap.add_argument("--hypo", type=int, default=1)
     ap.add_argument("--oil-steps", type=int, default=1000, help="OIL steps per pose (reference: 1000)")
-    ap.add_argument("--mode", default="split3", choices=["split3", "split2", "fp16", "fp32"])
+    ap.add_argument("--mode", default="split3", choices=["split3", "fp8lo", "split2", "fp16", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--dataset", default="h36m", choices=["h36m", "pw3d", "mini", "syrip"],
                     help="ZeDO config block (IPO key joints / axes / scale clamp; infant configs switch phase at 95%%)")

@@ -40,6 +40,8 @@ extern "C" {
 #define ZEDO_GEMM_FP16   1  /* tcgen05, single-pass fp16 inputs: fast mode             */
 #define ZEDO_GEMM_FP32   2  /* CUDA-core float32 FFMA: validation kernel                */
 #define ZEDO_GEMM_SPLIT2 3  /* tcgen05, fp16 activations x (hi+lo) weights: 2 MMA passes  */
+#define ZEDO_GEMM_FP8LO  4  /* tcgen05, fp16 main product + the two low-order products in e4m3 (kind::f8f6f4):
+                               2 fp16-pass equivalents, 2^-15 product error (split3: 2^-22, split2: 2^-12) */
 
 /* network kinds */
 #define ZEDO_NET_SCORE_FC_ADV 0  /* ScoreModelFC_Adv          (model.py:97-298)          */

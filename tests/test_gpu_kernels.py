@@ -122,7 +122,7 @@ def test_grad_field_empty_batch(zr, geom_kernel):
 
 
 # ---- score network (K1) -------------------------------------------------------------------------------
-@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("split3", 2e-5), ("fp16", 3e-3)])
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("split3", 2e-5), ("fp8lo", 4e-5), ("fp16", 3e-3)])
 def test_score_forward_golden(zr, golden, plan17, mode, tol):
     g = golden("net")
     for t in (0.1, 0.05, 0.01):
@@ -168,6 +168,9 @@ def test_score_forward_vs_oracle_ragged_batches(zr, plan17, B):
     assert rel_err(fp32, ref) < 2e-5
     assert rel_err(tc, ref) < 2e-5
     assert rel_err(tc, fp32) < 2e-5  # tcgen05 path against the CUDA-core validation kernel, on device
+    # fp16 main product + e4m3 low-order products (kind::f8f6f4 into the same accumulator): 2^-15 product error
+    f8 = plan17.forward(dev(x), 33.3, mode="fp8lo").cpu().numpy()
+    assert rel_err(f8, ref) < 4e-5 and rel_err(f8, fp32) < 4e-5
 
 
 def test_score_forward_j12_and_block_count(zr, golden):
@@ -189,7 +192,7 @@ def test_score_forward_j12_and_block_count(zr, golden):
     assert e.value.code == -2
 
 
-@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("split3", 2e-5)])
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("split3", 2e-5), ("fp8lo", 5e-5)])
 def test_control_network_forward_and_loop(zr, golden, mode, tol):
     """Control_ScoreModelFC_Adv (the infant network, control_model.py:277-382): forward against the golden
     vector recorded from the reference, a random batch against the oracle, and a few OIL steps with the
@@ -261,7 +264,7 @@ def test_oil_teacher_forced_golden(zr, golden, plan17, geom_kernel):
     assert rel_err(T.cpu().numpy(), g["T_out"].reshape(16, 3)) < 1e-5
 
 
-@pytest.mark.parametrize("mode", ["split3", "fp32"])
+@pytest.mark.parametrize("mode", ["split3", "fp8lo", "fp32"])
 def test_oil_teacher_forced_every_step(zr, golden, plan17, geom_kernel, mode):
     """Per-step parity (north_star: 1e-4 relative): every one of 60 consecutive steps across the phase
     switch, each restarted from the GPU's own previous state, against the oracle."""
@@ -338,7 +341,7 @@ def test_oil_full_loop_damped_network_golden(zr, golden):
     assert abs(m_gpu.mean() - gs["mpjpe"].mean()) < 5e-4
 
 
-@pytest.mark.parametrize("mode", ["split3", "fp32"])
+@pytest.mark.parametrize("mode", ["split3", "fp8lo", "fp32"])
 def test_c1_size_final_mpjpe_vs_reference(zr, golden, mode):
     """BASELINE configs[0] size: 1,024 poses, the reference's own IPO output (500 Adam iterations) fed to the
     1000-step loop.  north_star: final MPJPE within 0.1 mm -- the dataset-level mean over the 1,024 poses; single
@@ -370,7 +373,8 @@ def test_c1_size_final_mpjpe_vs_reference(zr, golden, mode):
     p.close()
 
 
-def test_oil_rows_are_independent(zr, plan17):
+@pytest.mark.parametrize("mode", ["split3", "fp8lo"])
+def test_oil_rows_are_independent(zr, plan17, mode):
     """Sharding property: running two halves separately is bit-identical to the full batch."""
     B = 1000
     ds = zo.make_synthetic_dataset(B, seed=3)
@@ -379,11 +383,12 @@ def test_oil_rows_are_independent(zr, plan17):
     T0 = dev(zo.init_translation(ds["db_2d"][:, :, :2], ds["camera_param"], 3.0).reshape(B, 3))
     ts = zo.oil_time_grid()[195:205]
     xa, Ta = x0.clone(), T0.clone()
-    plan17.oil_loop(xa, Ta, uv, K, conf.clone(), ts, phase_switch=5)
+    plan17.oil_loop(xa, Ta, uv, K, conf.clone(), ts, phase_switch=5, mode=mode)
     parts = []
     for lo, hi in ((0, 437), (437, B)):
         xb, Tb = x0[lo:hi].clone(), T0[lo:hi].clone()
-        plan17.oil_loop(xb, Tb, uv[lo:hi].contiguous(), K[lo:hi].contiguous(), conf[lo:hi].clone(), ts, phase_switch=5)
+        plan17.oil_loop(xb, Tb, uv[lo:hi].contiguous(), K[lo:hi].contiguous(), conf[lo:hi].clone(), ts, phase_switch=5,
+                        mode=mode)
         parts.append(xb)
     assert torch.equal(torch.cat(parts), xa)
 

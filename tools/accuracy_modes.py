@@ -23,7 +23,7 @@ gt = ds["db_3d"].astype(np.float64)
 res = {}
 dumps = [0, 9, 99, 199, 499, steps - 1]
 dumps = sorted(set(d for d in dumps if d < steps))
-for mode in ("fp32", "split3", "split2", "fp16"):
+for mode in ("fp32", "split3", "fp8lo", "split2", "fp16"):
     x, Tm = x_rot.clone(), T.clone()
     conf = t(ds["db_2d"][:, :, 2])
     torch.cuda.synchronize(); t0 = time.perf_counter()
@@ -33,7 +33,7 @@ for mode in ("fp32", "split3", "split2", "fp16"):
 def mp(x): return np.array([zo.mpjpe(x[n], gt[n]) for n in range(B)])
 base = res["fp32"]
 out = {"B": B, "steps": steps}
-for mode in ("split3", "split2", "fp16"):
+for mode in ("split3", "fp8lo", "split2", "fp16"):
     r = res[mode]
     drift = [float(np.abs(r["dump"][k] - base["dump"][k]).max() / np.abs(base["dump"][k]).max()) for k in range(len(dumps))]
     dm = mp(r["x"]) - mp(base["x"])
@@ -43,7 +43,7 @@ out["fp32"] = dict(sec=base["sec"], mpjpe_mean_m=float(mp(base["x"]).mean()))
 # oracle on a 64-pose subset, from the same (R, T)
 n = 64
 xo, To, _ = zo.oil_loop_schedule(W, x_rot.cpu().numpy()[:n], T.cpu().numpy()[:n].reshape(n, 1, 3), ds["db_2d"][:n, :, :2], ds["camera_param"][:n], ds["db_2d"][:n, :, 2].copy(), ts, steps // 5)
-for mode in ("fp32", "split3", "split2", "fp16"):
+for mode in ("fp32", "split3", "fp8lo", "split2", "fp16"):
     xm = res[mode]["x"][:n]
     dmo = np.array([zo.mpjpe(xm[i], gt[i]) - zo.mpjpe(xo[i], gt[i]) for i in range(n)])
     out[mode]["vs_oracle64"] = dict(drift=float(np.abs(xm - xo).max() / np.abs(xo).max()), mpjpe_diff_mm_mean=float(np.abs(dmo).mean() * 1e3), mpjpe_diff_mm_max=float(np.abs(dmo).max() * 1e3),

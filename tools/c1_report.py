@@ -22,7 +22,7 @@ ref = g["mpjpe"]
 out = {"poses": N, "oil_steps": 1000, "reference_mpjpe_m": float(ref.mean()),
        "reference_noise_floor": "numpy oracle vs the torch reference on the same inputs: aggregate 0.0005 mm, per-pose "
                                 "mean 0.144 mm, max 1.484 mm (tests/golden/PINNING.txt)"}
-for mode in ("split3", "fp32", "split2", "fp16"):
+for mode in ("split3", "fp32", "fp8lo", "split2", "fp16"):
     x, T = dev(np.einsum("bij,bnj->bni", g["R"], x0).astype(np.float32)), dev(g["T"].reshape(N, 3))
     plan.oil_loop(x, T, dev(uv), dev(K), dev(conf), zo.oil_time_grid(), mode=mode)
     err, _ = zr.eval_multi(x[:, None].contiguous(), gt)

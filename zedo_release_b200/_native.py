@@ -13,7 +13,7 @@ from typing import Dict, Iterable, Sequence
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libzedo_b200.so")
 
-GEMM_SPLIT3, GEMM_FP16, GEMM_FP32, GEMM_SPLIT2 = 0, 1, 2, 3
+GEMM_SPLIT3, GEMM_FP16, GEMM_FP32, GEMM_SPLIT2, GEMM_FP8LO = 0, 1, 2, 3, 4
 NET_SCORE_FC_ADV, NET_CONTROL = 0, 1
 PRED_EULER_MARUYAMA, PRED_REVERSE_DIFFUSION = 0, 1
 

@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda_fp8.h>
+
 #include "kernels.cuh"
 
 namespace zedo {
@@ -79,6 +81,44 @@ static int pack_weight(const float* w, int N, int K, int bn, PackedWeight* out) 
   return 0;
 }
 
+// CTA-pair operand of the ZEDO_GEMM_FP8LO mode: per (128-row half tile, k-block) the images [hi16 | hi8 | lo8]
+// (16 + 8 + 8 KiB) with hi8 = e4m3(hi16 * 2^-11) and lo8 = e4m3(lo16): the activation side carries the matching
+// lo8 = e4m3(lo16 * 2^11) and hi8 = e4m3(hi16), so all three products land in one accumulator at the same scale.
+static int pack_weight_f8(const float* w, int N, int K, PackedWeight* out) {
+  constexpr int rows = 128;
+  const int n_pad = (int)round_up(N, rows), k_pad = (int)round_up(K, kBlockK);
+  const int num_kb = k_pad / kBlockK;
+  const float s = pow2_scale_for(w, (int64_t)N * K);
+  const size_t blk_bytes = (size_t)rows * kBlockK * 4;  // 32 KiB
+  std::vector<uint8_t> buf((size_t)(n_pad / rows) * num_kb * blk_bytes, 0);
+  for (int n = 0; n < N; ++n) {
+    for (int k = 0; k < K; ++k) {
+      const float v = w[(int64_t)n * K + k] * s;
+      const __half hi = __float2half_rn(v);
+      const __half lo = __float2half_rn(v - __half2float(hi));
+      const int rt = n / rows, r = n % rows, kb = k / kBlockK, c = k % kBlockK;
+      uint8_t* blk = buf.data() + ((size_t)rt * num_kb + kb) * blk_bytes;
+      reinterpret_cast<__half*>(blk)[(c >> 3) * (rows * 8) + r * 8 + (c & 7)] = hi;
+      const size_t o8 = (size_t)(c >> 4) * (rows * 16) + (size_t)r * 16 + (c & 15);
+      blk[(size_t)rows * kBlockK * 2 + o8] =
+          (uint8_t)__nv_cvt_float_to_fp8(__half2float(hi) * (1.f / kLo8Scale), __NV_SATFINITE, __NV_E4M3);
+      blk[(size_t)rows * kBlockK * 3 + o8] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(lo), __NV_SATFINITE, __NV_E4M3);
+    }
+  }
+  ZEDO_CUDA_TRY(cudaMalloc(&out->dev, buf.size()));
+  const cudaError_t e = cudaMemcpy(out->dev, buf.data(), buf.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(out->dev);
+    out->dev = nullptr;
+    return (int)e;
+  }
+  out->descale = 1.f / s;
+  out->n_pad = n_pad;
+  out->k_pad = k_pad;
+  out->bn = rows;
+  return 0;
+}
+
 struct GemmOp {
   int weight;      // index into plan->packed / plan->w32
   int in_buf;      // -1 = xa (first operand), else activation buffer index
@@ -117,6 +157,7 @@ struct zedo_plan {
   std::vector<PackedWeight> packed;
   std::vector<PackedWeight> packed_pair;  // 1024 -> 1024 layers again, 128-row tiles for the CTA-pair kernel
   std::vector<PackedWeight> packed64;     // hidden-width layers again, 64-row tiles: small-batch latency mode
+  std::vector<PackedWeight> packed_f8;    // 1024 -> 1024 layers, [hi16 | hi8 | lo8] pair tiles (ZEDO_GEMM_FP8LO)
   int small_batch_tiles = 18;             // use the 64-wide tiles when the batch has at most this many 128-row tiles
   std::vector<GemmOp> program;
   bool use_pairs = true;
@@ -354,8 +395,14 @@ int net_forward(zedo_plan* p, const float* x, const float* tbl, int64_t B, int m
     }
     return 0;
   }
-  if (mode != ZEDO_GEMM_SPLIT3 && mode != ZEDO_GEMM_FP16 && mode != ZEDO_GEMM_SPLIT2) return ZEDO_E_INVALID;
-  const int nprod = mode == ZEDO_GEMM_SPLIT3 ? 3 : (mode == ZEDO_GEMM_SPLIT2 ? 2 : 1);
+  if (mode != ZEDO_GEMM_SPLIT3 && mode != ZEDO_GEMM_FP16 && mode != ZEDO_GEMM_SPLIT2 && mode != ZEDO_GEMM_FP8LO)
+    return ZEDO_E_INVALID;
+  // FP8LO: the 1024 -> 1024 layers run 1 fp16 + 2 e4m3 products on format-1 activation blocks (CTA-pair kernel at
+  // every batch size, so a pose's result does not depend on the batch it travels in); the K = 64 first layer and
+  // post_dense keep the three fp16 products and only read / write the format-1 blocks.
+  const bool f8 = mode == ZEDO_GEMM_FP8LO;
+  if (f8 && !p->use_pairs) return ZEDO_E_INVALID;
+  const int nprod = (mode == ZEDO_GEMM_SPLIT3 || f8) ? 3 : (mode == ZEDO_GEMM_SPLIT2 ? 2 : 1);
   if (!xa_ready && (rc = launch_pack_x(x, p->xa, B, p->D, st))) return rc;
   for (const GemmOp& op : p->program) {
     const PackedWeight& w = p->packed[op.weight];
@@ -375,11 +422,18 @@ int net_forward(zedo_plan* p, const float* x, const float* tbl, int64_t B, int m
     a.num_kb = w.k_pad / kBlockK;
     a.descale = w.descale;
     a.gn_eps = p->desc.gn_eps;
+    a.a_fmt = (f8 && op.in_buf >= 0) ? 1 : 0;  // xa (first operand) is always a format-0 block
+    a.o_fmt = f8 ? 1 : 0;
     {
       ProfScope ps(p, op.epi == EPI_LINEAR_F32 ? 2 : (a.num_kb == 1 ? 0 : 1), st);
       const PackedWeight& wp = p->packed_pair[op.weight];
       const PackedWeight& w64 = p->packed64[op.weight];
-      if (m_tiles <= p->small_batch_tiles && w64.dev != nullptr && op.epi != EPI_LINEAR_F32) {
+      const PackedWeight& w8 = p->packed_f8[op.weight];
+      if (f8 && w8.dev != nullptr && op.epi != EPI_LINEAR_F32) {
+        a.W = w8.dev;
+        a.m_tiles = (m_tiles + 1) & ~1;
+        rc = launch_layer_tc2(a, 4, op.epi, p->num_sms, st);
+      } else if (m_tiles <= p->small_batch_tiles && w64.dev != nullptr && op.epi != EPI_LINEAR_F32) {
         a.W = w64.dev;  // few poses: 64-channel tiles keep all SMs busy and cut the per-tile MMA chain by 4
         a.n_tiles = w64.n_pad / 64;
         rc = launch_layer_tc(a, 64, nprod, op.epi, p->num_sms, st);
@@ -498,7 +552,7 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
   auto add_weight = [&](const std::string& name, int N, int K, int bn) -> int {
     const std::vector<float>* w = tm.get(name + ".weight", (size_t)N * K);
     if (!w) return ZEDO_E_MISSING;
-    PackedWeight pw, pw2, pw64;
+    PackedWeight pw, pw2, pw64, pw8;
     int r = pack_weight(w->data(), N, K, bn, &pw);
     if (r) return r > 0 ? -1000 - r : r;
     p->owned.push_back(pw.dev);
@@ -510,11 +564,14 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
     if (K == H && N == H) {
       if ((r = pack_weight(w->data(), N, K, 128, &pw2))) return r > 0 ? -1000 - r : r;
       p->owned.push_back(pw2.dev);
+      if ((r = pack_weight_f8(w->data(), N, K, &pw8))) return r > 0 ? -1000 - r : r;
+      p->owned.push_back(pw8.dev);
     }
     float* w32 = nullptr;
     if ((r = upload(p, &w32, w->data(), w->size()))) return r > 0 ? -1000 - r : r;
     p->packed.push_back(pw);
     p->packed_pair.push_back(pw2);
+    p->packed_f8.push_back(pw8);
     p->w32.push_back(w32);
     p->w_n.push_back(N);
     p->w_k.push_back(K);
@@ -684,7 +741,7 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
   PLAN_TRY(dev_alloc(p, &p->xa, (size_t)p->m_pad * kBlockK * 2));
   for (int i = 0; i < p->n_act; ++i) {
     __half* a = nullptr;
-    PLAN_TRY(dev_alloc(p, &a, (size_t)p->m_pad * H * 2));
+    PLAN_TRY(dev_alloc(p, &a, (size_t)p->m_pad * H * 3));  // room for format-1 blocks (48 KiB per 128 x 64)
     p->act.push_back(a);
   }
   PLAN_TRY(dev_alloc(p, &p->eps, (size_t)p->m_pad * 64));

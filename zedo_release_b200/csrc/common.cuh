@@ -74,6 +74,22 @@ __host__ __device__ inline int64_t blocked_half_offset(int64_t row, int64_t col,
   return ((rt * num_kb + kb) * 2 + hl) * image + (c >> 3) * ((int64_t)tile_rows * 8) + r * 8 + (c & 7);
 }
 
+// Activation block formats.  A block is the 128 x 64 slice (row tile, k-block) of an activation matrix:
+//   format 0  [hi16 | lo16]                2 x 16 KiB   v = hi16 + lo16 (fp16 pair, ~22 bits)
+//   format 1  [hi16 | hi8 | lo8 | lo16]    16 + 8 + 8 + 16 KiB, used by the ZEDO_GEMM_FP8LO mode:
+//             hi8 = e4m3(hi16), lo8 = e4m3(lo16 * 2^11) are the operands of the two low-order products, which only
+//             need ~4 bits (they sit 2^-11 below the main product) and run at twice the fp16 MMA rate;
+//             the first 32 KiB are what a GEMM stage loads (one bulk copy), lo16 is kept for the consumers that add
+//             the activation itself (residual / addend epilogues, post_dense).
+// An 8-bit image uses the same interleaved layout with 16 elements per 16-byte chunk:
+// byte offset = (c / 16) * (rows * 16) + r * 16 + c % 16.
+constexpr int kImgHalves = kActTileRows * kBlockK;  // one fp16 image of a block (16 KiB)
+__host__ __device__ constexpr int act_block_halves(int fmt) { return fmt ? 3 * kImgHalves : 2 * kImgHalves; }
+__host__ __device__ constexpr int act_lo16_off(int fmt) { return fmt ? 2 * kImgHalves : kImgHalves; }  // in halves
+constexpr int kHi8ByteOff = kImgHalves * 2;             // byte offset of the hi8 image inside a format-1 block
+constexpr int kLo8ByteOff = kImgHalves * 2 + kImgHalves;  // ... of the lo8 image
+constexpr float kLo8Scale = 2048.f;                     // lo8 = e4m3(lo * 2^11); the matching W image carries 2^-11
+
 __host__ __device__ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
 // ---- hi/lo split --------------------------------------------------------------------------------

@@ -19,6 +19,8 @@ struct LayerArgs {
   float descale;
   float gn_eps;
   int dbg;  // timing experiments only (env ZEDO_DBG): 1 = no bulk copies after the first fill, 2 = no MMAs
+  int a_fmt;  // block format of A (common.cuh): 0 = [hi16 | lo16], 1 = [hi16 | hi8 | lo8 | lo16]
+  int o_fmt;  // block format of out / resid / addend
 };
 constexpr int EPI_GN_SILU = 0, EPI_LINEAR_ACT = 1, EPI_LINEAR_F32 = 2;
 int launch_layer_tc(const LayerArgs& a, int bn, int nprod, int epi, int num_sms, cudaStream_t st);

@@ -86,7 +86,8 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) layer_tc_kernel(const Layer
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile / args.n_tiles, nt = tile - mt * args.n_tiles;
-        const __half* a_src = args.A + ((int64_t)mt * num_kb) * 2 * (kActTileRows * kBlockK);
+        const int64_t a_blk = act_block_halves(args.a_fmt);
+        const __half* a_src = args.A + ((int64_t)mt * num_kb) * a_blk;
         const __half* w_src = args.W + ((int64_t)nt * num_kb) * 2 * (BN * kBlockK);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -94,8 +95,14 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) layer_tc_kernel(const Layer
             mbar_arrive(&full[stage]);  // experiment: MMA on stale tiles, no L2->SMEM traffic
           } else {
             mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-            bulk_g2s(sA + stage * Cfg::kABytes, a_src + (int64_t)kb * 2 * (kActTileRows * kBlockK), Cfg::kABytes,
-                     &full[stage]);
+            if (NPROD == 3 && args.a_fmt == 1) {
+              // format-1 block: hi16 and lo16 are not adjacent (the 8-bit images sit between them)
+              bulk_g2s(sA + stage * Cfg::kABytes, a_src + (int64_t)kb * a_blk, Cfg::kAImage, &full[stage]);
+              bulk_g2s(sA + stage * Cfg::kABytes + Cfg::kAImage, a_src + (int64_t)kb * a_blk + act_lo16_off(1),
+                       Cfg::kAImage, &full[stage]);
+            } else {
+              bulk_g2s(sA + stage * Cfg::kABytes, a_src + (int64_t)kb * a_blk, Cfg::kABytes, &full[stage]);
+            }
             bulk_g2s(sB + stage * Cfg::kBBytes, w_src + (int64_t)kb * 2 * (BN * kBlockK), Cfg::kBBytes,
                      &full[stage]);
           }

@@ -31,6 +31,18 @@ __device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t adesc, u
 }
 
 // arrive (once all prior MMAs of this thread retire) on the barrier at this offset in both CTAs
+// the same for 8-bit operands (e4m3 x e4m3, K = 32 per instruction, twice the fp16 rate); kind::f8f6f4 shares the
+// instruction-descriptor layout of kind::f16 and its format code 0 is E4M3, so make_idesc_f16 serves both
+__device__ __forceinline__ void umma_f8_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -55,8 +67,10 @@ struct PairCfg {
   static constexpr int kHalfN = 128;                           // W rows staged by each CTA
   static constexpr int kAImage = kActTileRows * kBlockK * 2;   // 16 KiB
   static constexpr int kBImage = kHalfN * kBlockK * 2;         // 16 KiB
-  static constexpr int kABytes = kAImage * (NPROD == 3 ? 2 : 1);
-  static constexpr int kBBytes = kBImage * (NPROD >= 2 ? 2 : 1);
+  // NPROD = 4 (ZEDO_GEMM_FP8LO): A_hi16.W_hi16 in fp16 + A_lo8.W_hi8 + A_hi8.W_lo8 in e4m3; a stage holds the
+  // [hi16 | hi8 | lo8] images of both operands (format-1 blocks, common.cuh) = 32 KiB each
+  static constexpr int kABytes = NPROD == 4 ? 2 * kAImage : kAImage * (NPROD == 3 ? 2 : 1);
+  static constexpr int kBBytes = NPROD == 4 ? 2 * kBImage : kBImage * (NPROD >= 2 ? 2 : 1);
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kMaxStages = (225 * 1024) / kStageBytes;
   static constexpr int kStages = kMaxStages > 6 ? 6 : kMaxStages;
@@ -120,13 +134,14 @@ layer_tc2_kernel(const LayerArgs args) {
       for (int pt = pair0; pt < num_pairs; pt += pair_stride) {
         const int mp = pt / args.n_tiles, nt = pt - mp * args.n_tiles;
         const int mt = 2 * mp + (int)rank;
-        const __half* a_src = args.A + ((int64_t)mt * num_kb) * 2 * (kActTileRows * kBlockK);
+        // an A block is 32 KiB (format 0) or 48 KiB (format 1); either way the stage takes its first kABytes
+        const int64_t a_blk = act_block_halves(args.a_fmt);
+        const __half* a_src = args.A + ((int64_t)mt * num_kb) * a_blk;
         const __half* w_src = args.W + ((int64_t)(2 * nt + (int)rank) * num_kb) * 2 * (Cfg::kHalfN * kBlockK);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-          bulk_g2s(sA + stage * Cfg::kABytes, a_src + (int64_t)kb * 2 * (kActTileRows * kBlockK), Cfg::kABytes,
-                   &full[stage]);
+          bulk_g2s(sA + stage * Cfg::kABytes, a_src + (int64_t)kb * a_blk, Cfg::kABytes, &full[stage]);
           bulk_g2s(sB + stage * Cfg::kBBytes, w_src + (int64_t)kb * 2 * (Cfg::kHalfN * kBlockK), Cfg::kBBytes,
                    &full[stage]);
           if (++stage == S) {
@@ -162,13 +177,26 @@ layer_tc2_kernel(const LayerArgs args) {
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
               umma_f16_2cta(d_tmem, a_hi + kAStep * k, b_hi + kBStep * k, idesc, (kb | k) != 0);
+            if (NPROD == 4) {
+              // 64 e4m3 columns = four 16-byte chunks = two K = 32 instructions per product; same chunk strides
+              const uint64_t a_hi8 = make_kmajor_desc(a_addr + Cfg::kAImage, kActTileRows);
+              const uint64_t a_lo8 = make_kmajor_desc(a_addr + Cfg::kAImage + Cfg::kAImage / 2, kActTileRows);
+              const uint64_t b_hi8 = make_kmajor_desc(b_addr + Cfg::kBImage, Cfg::kHalfN);
+              const uint64_t b_lo8 = make_kmajor_desc(b_addr + Cfg::kBImage + Cfg::kBImage / 2, Cfg::kHalfN);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 32; ++k)
+                umma_f8_2cta(d_tmem, a_lo8 + kAStep * k, b_hi8 + kBStep * k, idesc, 1);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 32; ++k)
+                umma_f8_2cta(d_tmem, a_hi8 + kAStep * k, b_lo8 + kBStep * k, idesc, 1);
+            }
             if (NPROD == 3) {
               const uint64_t a_lo = make_kmajor_desc(a_addr + Cfg::kAImage, kActTileRows);
 #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k)
                 umma_f16_2cta(d_tmem, a_lo + kAStep * k, b_hi + kBStep * k, idesc, 1);
             }
-            if (NPROD >= 2) {
+            if (NPROD == 2 || NPROD == 3) {
               const uint64_t b_lo = make_kmajor_desc(b_addr + Cfg::kBImage, Cfg::kHalfN);
 #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k)
@@ -252,6 +280,7 @@ static int launch_pair_nprod(const LayerArgs& a, int nprod, int num_sms, cudaStr
     case 3: return launch_pair<3, EPI>(a, num_sms, st);
     case 2: return launch_pair<2, EPI>(a, num_sms, st);
     case 1: return launch_pair<1, EPI>(a, num_sms, st);
+    case 4: return a.a_fmt == 1 ? launch_pair<4, EPI>(a, num_sms, st) : ZEDO_E_INVALID;
     default: return ZEDO_E_INVALID;
   }
 }

@@ -3,6 +3,8 @@
 #pragma once
 #include <cstdlib>
 
+#include <cuda_fp8.h>
+
 #include "kernels.cuh"
 
 namespace zedo {
@@ -148,6 +150,19 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// four halves (two packed half2 words, optionally scaled by 2^11) -> four e4m3 bytes, element order kept
+__device__ __forceinline__ uint32_t half2x2_to_e4m3x4(uint32_t a, uint32_t b, bool scale) {
+  __half2 ha = *reinterpret_cast<const __half2*>(&a), hb = *reinterpret_cast<const __half2*>(&b);
+  if (scale) {
+    const __half2 s = __float2half2_rn(kLo8Scale);
+    ha = __hmul2(ha, s);
+    hb = __hmul2(hb, s);
+  }
+  const uint32_t lo = __nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(ha), __NV_SATFINITE, __NV_E4M3);
+  const uint32_t hi = __nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(hb), __NV_SATFINITE, __NV_E4M3);
+  return lo | (hi << 16);
+}
+
 __device__ __forceinline__ void add_hi_lo(float* v, const uint4& h4, const uint4& l4) {
   const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
@@ -187,7 +202,8 @@ __device__ __forceinline__ void epilogue_tile(const LayerArgs& args, uint32_t tm
   static_assert(kGroupsPerWarp >= 1, "too many epilogue warps for this tile width");
   const int n_total = args.n_tiles * BN;
   const int nkb_out = n_total / kBlockK;
-  constexpr int64_t kLoOff = kActTileRows * kBlockK;
+  const int64_t kBlk = act_block_halves(args.o_fmt);  // halves per (row tile, k-block) block of out / resid / addend
+  const int64_t kLoOff = act_lo16_off(args.o_fmt);    // lo16 image inside the block
 #pragma unroll 1
   for (int gg = 0; gg < kGroupsPerWarp; ++gg) {
     const int g = chalf * kGroupsPerWarp + gg;
@@ -196,8 +212,7 @@ __device__ __forceinline__ void epilogue_tile(const LayerArgs& args, uint32_t tm
     const int kbo = col0 / kBlockK;
     const int hsel = (col0 / 32) & 1;
     // chunk c of this row lives at c * (128 rows * 8 halves) + r * 8 inside the (mt, kbo) hi image
-    const int64_t row_off =
-        (((int64_t)mt * nkb_out + kbo) * 2) * (kActTileRows * kBlockK) + (int64_t)r * 8;
+    const int64_t row_off = ((int64_t)mt * nkb_out + kbo) * kBlk + (int64_t)r * 8;
     constexpr int kChunkStride = kActTileRows * 8;
     // residual / addend loads are issued before the TMEM read so their latency overlaps it
     uint4 rh[4], rl[4];
@@ -277,14 +292,42 @@ __device__ __forceinline__ void epilogue_tile(const LayerArgs& args, uint32_t tm
 #pragma unroll
       for (int j = 0; j < 4; ++j) add_hi_lo(v + 8 * j, rh[j], rl[j]);
     }
+    if (args.o_fmt == 0) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint32_t hi[4], lo[4];
+      for (int j = 0; j < 4; ++j) {
+        uint32_t hi[4], lo[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) split_pair(v[8 * j + 2 * e], v[8 * j + 2 * e + 1], hi[e], lo[e]);
-      const int pc = (hsel * 4 + j) * kChunkStride;
-      *reinterpret_cast<uint4*>(args.out + row_off + pc) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(args.out + row_off + kLoOff + pc) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        for (int e = 0; e < 4; ++e) split_pair(v[8 * j + 2 * e], v[8 * j + 2 * e + 1], hi[e], lo[e]);
+        const int pc = (hsel * 4 + j) * kChunkStride;
+        *reinterpret_cast<uint4*>(args.out + row_off + pc) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(args.out + row_off + kLoOff + pc) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    } else {
+      // format 1: hi16, lo16 as above plus the e4m3 images hi8 = e4m3(hi16), lo8 = e4m3(lo16 * 2^11); one 16-byte
+      // chunk of an 8-bit image holds 16 columns of this row
+      uint8_t* blk8 = reinterpret_cast<uint8_t*>(args.out + ((int64_t)mt * nkb_out + kbo) * kBlk) + r * 16;
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        uint32_t h8[4], l8[4];
+#pragma unroll
+        for (int j2 = 0; j2 < 2; ++j2) {
+          const int j = 2 * jj + j2;
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) split_pair(v[8 * j + 2 * e], v[8 * j + 2 * e + 1], hi[e], lo[e]);
+          const int pc = (hsel * 4 + j) * kChunkStride;
+          *reinterpret_cast<uint4*>(args.out + row_off + pc) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(args.out + row_off + kLoOff + pc) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            h8[2 * j2 + w] = half2x2_to_e4m3x4(hi[2 * w], hi[2 * w + 1], false);
+            l8[2 * j2 + w] = half2x2_to_e4m3x4(lo[2 * w], lo[2 * w + 1], true);
+          }
+        }
+        const int pc8 = (hsel * 2 + jj) * (kActTileRows * 16);
+        *reinterpret_cast<uint4*>(blk8 + kHi8ByteOff + pc8) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+        *reinterpret_cast<uint4*>(blk8 + kLo8ByteOff + pc8) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
+      }
     }
   }
 }

@@ -15,7 +15,8 @@ import torch
 
 from . import _native as nat
 
-GEMM_MODES = {"split3": nat.GEMM_SPLIT3, "split2": nat.GEMM_SPLIT2, "fp16": nat.GEMM_FP16, "fp32": nat.GEMM_FP32}
+GEMM_MODES = {"split3": nat.GEMM_SPLIT3, "split2": nat.GEMM_SPLIT2, "fp16": nat.GEMM_FP16, "fp32": nat.GEMM_FP32,
+              "fp8lo": nat.GEMM_FP8LO}
 
 
 def _mode(mode) -> int:
