@@ -140,6 +140,14 @@ layer_tc2_kernel(const LayerArgs args) {
         const __half* w_src = args.W + ((int64_t)(2 * nt + (int)rank) * num_kb) * 2 * (Cfg::kHalfN * kBlockK);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
+          if ((args.dbg & 1) && (pt != pair0 || kb >= S)) {
+            mbar_arrive(&full[stage]);  // experiment: MMA on stale tiles, no L2 -> SMEM traffic
+            if (++stage == S) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
           bulk_g2s(sA + stage * Cfg::kABytes, a_src + (int64_t)kb * a_blk, Cfg::kABytes, &full[stage]);
           bulk_g2s(sB + stage * Cfg::kBBytes, w_src + (int64_t)kb * 2 * (Cfg::kHalfN * kBlockK), Cfg::kBBytes,
@@ -286,7 +294,10 @@ static int launch_pair_nprod(const LayerArgs& a, int nprod, int num_sms, cudaStr
 }
 
 // hidden layers (N multiple of 256, weights packed with 128-row tiles); a.m_tiles must be even
-int launch_layer_tc2(const LayerArgs& a, int nprod, int epi, int num_sms, cudaStream_t st) {
+int launch_layer_tc2(const LayerArgs& a_in, int nprod, int epi, int num_sms, cudaStream_t st) {
+  static const int dbg = getenv("ZEDO_DBG") ? atoi(getenv("ZEDO_DBG")) : 0;
+  LayerArgs a = a_in;
+  a.dbg = dbg;
   if (epi == EPI_GN_SILU) return launch_pair_nprod<EPI_GN_SILU>(a, nprod, num_sms, st);
   if (epi == EPI_LINEAR_ACT) return launch_pair_nprod<EPI_LINEAR_ACT>(a, nprod, num_sms, st);
   return ZEDO_E_INVALID;
