@@ -289,8 +289,9 @@ def run_gpu_arm(args):
         line = {
             "metric": METRIC, "value": value, "unit": "poses/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp16 hi/lo 3-product split on tcgen05, f32 accumulate)"
-            if args.mode == "split3" else args.mode, "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": {"split3": "f32 (fp16 hi/lo 3-product split on tcgen05, f32 accumulate)",
+                                                         "fp8lo": "f32 (fp16 main product + e4m3 low-order products on tcgen05, f32 accumulate)"
+                                                         }.get(args.mode, args.mode), "data": "synthetic",
             "config": {"workload": f"{args.dataset} J={J} hypo={S}, {B} synthetic poses per GPU, random-init "
                                    f"{'control (infant)' if control else 'concat'} score net"
                                    f"{' (BASELINE configs[1])' if (args.dataset, J, S, B, control) == ('h36m', 17, 1, 262144, False) else ''}"
@@ -302,12 +303,13 @@ def run_gpu_arm(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "layer_tc2_kernel<3,GN_SILU> (1024x1024 hidden layer, tcgen05 cta_group::2)",
+            "roofline": {"bound": "tensor", "kernel": f"layer_tc2_kernel<{ {'split3': 3, 'fp8lo': 4, 'split2': 2, 'fp16': 1}.get(args.mode, 0) },GN_SILU> "
+                                                     "(1024x1024 hidden layer, tcgen05 cta_group::2)",
                          "achieved": achieved_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": (achieved_tflops / peaks["tflops"]) if achieved_tflops else None,
                          "traffic": ncu_traffic, "peak_source": peaks["src"],
                          "algorithmic_flop_per_launch": FLOP_PER_POSE_HIDDEN_LAYER * B,
-                         "mma_issue_factor": 3 if args.mode == "split3" else 1,
+                         "mma_issue_factor": {"split3": 3, "fp8lo": 2, "split2": 2}.get(args.mode, 1),
                          "avg_launch_ms": hid_ms, "launches_timed": hid_n,
                          "other_kernels_ms": {k: v[0] for k, v in prof.items() if k != "hidden_layer"}},
             "oil_pose_steps_per_s": B * world * args.oil_steps * S / (ms_total / args.steps / 1e3),
