@@ -67,3 +67,14 @@ def test_blocked_layout_is_an_interleaved_bijection(built_lib):
     assert built_lib.blocked_offset(0, 0, cols, tile, 1) - built_lib.blocked_offset(0, 0, cols, tile, 0) == 16384
     assert built_lib.blocked_offset(0, 64, cols, tile, 0) == 32768
     assert built_lib.blocked_offset(128, 0, cols, tile, 0) == 65536
+
+
+def test_mode_constants_match_the_header(built_lib):
+    """The Python binding's GEMM-mode / predictor / network-kind constants are the header's."""
+    text = open(os.path.join(ROOT, "include", "zedo_b200.h")).read()
+    defs = {k: int(v) for k, v in re.findall(r"#define\s+(ZEDO_[A-Z0-9_]+)\s+(-?\d+)\b", text)}
+    from zedo_release_b200 import engine
+    for name, value in engine.GEMM_MODES.items():
+        assert defs[f"ZEDO_GEMM_{name.upper()}"] == value
+    assert sorted(engine.GEMM_MODES.values()) == sorted(v for k, v in defs.items() if k.startswith("ZEDO_GEMM_"))
+    assert defs["ZEDO_NET_SCORE_FC_ADV"] == built_lib.NET_SCORE_FC_ADV and defs["ZEDO_NET_CONTROL"] == built_lib.NET_CONTROL
