@@ -275,7 +275,11 @@ def run_gpu_arm(args):
     if os.path.exists(tp):
         try:
             with open(tp) as f:
-                ncu_traffic = json.load(f).get("hidden_layer_dram_bytes_per_launch")
+                summ = json.load(f)
+            # the captured figure belongs to the default mode's kernel at the default size; fp8lo has its own
+            key = {"split3": "hidden_layer_dram_bytes_per_launch",
+                   "fp8lo": "hidden_layer_fp8lo_dram_bytes_per_launch"}.get(args.mode)
+            ncu_traffic = summ.get(key) if (key and B == 262144) else None
         except Exception:
             ncu_traffic = None
     h2d = h_db2d.numel() * 4 + h_K.numel() * 4 + h_cl.numel() * 4
