@@ -552,9 +552,11 @@ def test_hypothesis_batching_is_exact(zr, plan17):
     assert not torch.equal(stacked[:, 0], stacked[:, 1])
 
 
-def test_full_size_batch_properties(zr):
+@pytest.mark.parametrize("mode,tol", [("split3", 2e-5), ("fp8lo", 4e-5)])
+def test_full_size_batch_properties(zr, mode, tol):
     """BASELINE configs[1] size (262,144 poses): sampled rows of the tcgen05 forward against the oracle, and a
-    3-step OIL loop on the full batch equals the same rows run on their own (row independence, bit-exact)."""
+    3-step OIL loop on the full batch (CTA-pair kernel) equals the same rows run on their own (64-channel
+    small-batch tiles): row independence, bit-exact, in both parity-grade GEMM modes."""
     B = 262144
     W = zo.make_weights(seed=0)
     p = zr.ScorePlan(W, n_joints=17, max_batch=B, device=0)
@@ -563,20 +565,20 @@ def test_full_size_batch_properties(zr):
     rep = B // 4096
     x = np.tile(ds["db_3d"], (rep, 1, 1)).astype(np.float32) + rng.normal(0, 0.02, (B, 17, 3)).astype(np.float32)
     xg = dev(x)
-    out = p.forward(xg, 55.5, mode="split3")
+    out = p.forward(xg, 55.5, mode=mode)
     assert torch.isfinite(out).all()
     rows = rng.choice(B, 256, replace=False)
     ref = zo.score_forward(W, x[rows], np.float32(55.5))
-    assert rel_err(out[rows].cpu().numpy(), ref) < 2e-5
+    assert rel_err(out[rows].cpu().numpy(), ref) < tol
     uv, K, conf = (dev(np.tile(ds[k], (rep, 1, 1))) for k in ("db_2d", "camera_param", "db_2d"))
     uv, conf = uv[:, :, :2].contiguous(), conf[:, :, 2].contiguous()
     T = dev(np.tile(zo.init_translation(ds["db_2d"][:, :, :2], ds["camera_param"], 3.0).reshape(4096, 3), (rep, 1)))
     ts = zo.oil_time_grid()[199:202]
     xa, Ta = xg.clone(), T.clone()
-    p.oil_loop(xa, Ta, uv, K, conf.clone(), ts, phase_switch=1)
+    p.oil_loop(xa, Ta, uv, K, conf.clone(), ts, phase_switch=1, mode=mode)
     sel = torch.tensor(np.sort(rows), device="cuda")
     xb, Tb = xg[sel].clone(), T[sel].clone()
-    p.oil_loop(xb, Tb, uv[sel].contiguous(), K[sel].contiguous(), conf[sel].clone(), ts, phase_switch=1)
+    p.oil_loop(xb, Tb, uv[sel].contiguous(), K[sel].contiguous(), conf[sel].clone(), ts, phase_switch=1, mode=mode)
     assert torch.equal(xa[sel], xb) and torch.equal(Ta[sel], Tb)
     p.close()
 

@@ -81,15 +81,14 @@ static int pack_weight(const float* w, int N, int K, int bn, PackedWeight* out) 
   return 0;
 }
 
-// CTA-pair operand of the ZEDO_GEMM_FP8LO mode: per (128-row half tile, k-block) the images [hi16 | hi8 | lo8]
-// (16 + 8 + 8 KiB) with hi8 = e4m3(hi16 * 2^-11) and lo8 = e4m3(lo16): the activation side carries the matching
+// Weight operand of the ZEDO_GEMM_FP8LO mode: per (`rows`-row tile, k-block) the images [hi16 | hi8 | lo8]
+// (rows = 128: CTA-pair half tiles, 16 + 8 + 8 KiB; rows = 64: small-batch tiles) with hi8 = e4m3(hi16 * 2^-11) and lo8 = e4m3(lo16): the activation side carries the matching
 // lo8 = e4m3(lo16 * 2^11) and hi8 = e4m3(hi16), so all three products land in one accumulator at the same scale.
-static int pack_weight_f8(const float* w, int N, int K, PackedWeight* out) {
-  constexpr int rows = 128;
+static int pack_weight_f8(const float* w, int N, int K, int rows, PackedWeight* out) {
   const int n_pad = (int)round_up(N, rows), k_pad = (int)round_up(K, kBlockK);
   const int num_kb = k_pad / kBlockK;
   const float s = pow2_scale_for(w, (int64_t)N * K);
-  const size_t blk_bytes = (size_t)rows * kBlockK * 4;  // 32 KiB
+  const size_t blk_bytes = (size_t)rows * kBlockK * 4;  // 32 KiB for 128 rows
   std::vector<uint8_t> buf((size_t)(n_pad / rows) * num_kb * blk_bytes, 0);
   for (int n = 0; n < N; ++n) {
     for (int k = 0; k < K; ++k) {
@@ -158,6 +157,7 @@ struct zedo_plan {
   std::vector<PackedWeight> packed_pair;  // 1024 -> 1024 layers again, 128-row tiles for the CTA-pair kernel
   std::vector<PackedWeight> packed64;     // hidden-width layers again, 64-row tiles: small-batch latency mode
   std::vector<PackedWeight> packed_f8;    // 1024 -> 1024 layers, [hi16 | hi8 | lo8] pair tiles (ZEDO_GEMM_FP8LO)
+  std::vector<PackedWeight> packed64_f8;  // the same with 64-row tiles: small-batch form of the fp8lo layers
   int small_batch_tiles = 18;             // use the 64-wide tiles when the batch has at most this many 128-row tiles
   std::vector<GemmOp> program;
   bool use_pairs = true;
@@ -397,9 +397,10 @@ int net_forward(zedo_plan* p, const float* x, const float* tbl, int64_t B, int m
   }
   if (mode != ZEDO_GEMM_SPLIT3 && mode != ZEDO_GEMM_FP16 && mode != ZEDO_GEMM_SPLIT2 && mode != ZEDO_GEMM_FP8LO)
     return ZEDO_E_INVALID;
-  // FP8LO: the 1024 -> 1024 layers run 1 fp16 + 2 e4m3 products on format-1 activation blocks (CTA-pair kernel at
-  // every batch size, so a pose's result does not depend on the batch it travels in); the K = 64 first layer and
-  // post_dense keep the three fp16 products and only read / write the format-1 blocks.
+  // FP8LO: the 1024 -> 1024 layers run 1 fp16 + 2 e4m3 products on format-1 activation blocks (CTA-pair kernel, or
+  // 64-channel tiles of the one-CTA kernel for small batches: same products, same order, so a pose's result does not
+  // depend on the batch it travels in); the K = 64 first layer and post_dense keep the three fp16 products and only
+  // read / write the format-1 blocks.
   const bool f8 = mode == ZEDO_GEMM_FP8LO;
   if (f8 && !p->use_pairs) return ZEDO_E_INVALID;
   const int nprod = (mode == ZEDO_GEMM_SPLIT3 || f8) ? 3 : (mode == ZEDO_GEMM_SPLIT2 ? 2 : 1);
@@ -430,9 +431,16 @@ int net_forward(zedo_plan* p, const float* x, const float* tbl, int64_t B, int m
       const PackedWeight& w64 = p->packed64[op.weight];
       const PackedWeight& w8 = p->packed_f8[op.weight];
       if (f8 && w8.dev != nullptr && op.epi != EPI_LINEAR_F32) {
-        a.W = w8.dev;
-        a.m_tiles = (m_tiles + 1) & ~1;
-        rc = launch_layer_tc2(a, 4, op.epi, p->num_sms, st);
+        const PackedWeight& w8s = p->packed64_f8[op.weight];
+        if (m_tiles <= p->small_batch_tiles && w8s.dev != nullptr) {
+          a.W = w8s.dev;  // few poses: 64-channel tiles, same three products in the same order (bit-identical)
+          a.n_tiles = w8s.n_pad / 64;
+          rc = launch_layer_tc(a, 64, 4, op.epi, p->num_sms, st);
+        } else {
+          a.W = w8.dev;
+          a.m_tiles = (m_tiles + 1) & ~1;
+          rc = launch_layer_tc2(a, 4, op.epi, p->num_sms, st);
+        }
       } else if (m_tiles <= p->small_batch_tiles && w64.dev != nullptr && op.epi != EPI_LINEAR_F32) {
         a.W = w64.dev;  // few poses: 64-channel tiles keep all SMs busy and cut the per-tile MMA chain by 4
         a.n_tiles = w64.n_pad / 64;
@@ -552,7 +560,7 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
   auto add_weight = [&](const std::string& name, int N, int K, int bn) -> int {
     const std::vector<float>* w = tm.get(name + ".weight", (size_t)N * K);
     if (!w) return ZEDO_E_MISSING;
-    PackedWeight pw, pw2, pw64, pw8;
+    PackedWeight pw, pw2, pw64, pw8, pw8s;
     int r = pack_weight(w->data(), N, K, bn, &pw);
     if (r) return r > 0 ? -1000 - r : r;
     p->owned.push_back(pw.dev);
@@ -564,14 +572,17 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
     if (K == H && N == H) {
       if ((r = pack_weight(w->data(), N, K, 128, &pw2))) return r > 0 ? -1000 - r : r;
       p->owned.push_back(pw2.dev);
-      if ((r = pack_weight_f8(w->data(), N, K, &pw8))) return r > 0 ? -1000 - r : r;
+      if ((r = pack_weight_f8(w->data(), N, K, 128, &pw8))) return r > 0 ? -1000 - r : r;
       p->owned.push_back(pw8.dev);
+      if ((r = pack_weight_f8(w->data(), N, K, 64, &pw8s))) return r > 0 ? -1000 - r : r;
+      p->owned.push_back(pw8s.dev);
     }
     float* w32 = nullptr;
     if ((r = upload(p, &w32, w->data(), w->size()))) return r > 0 ? -1000 - r : r;
     p->packed.push_back(pw);
     p->packed_pair.push_back(pw2);
     p->packed_f8.push_back(pw8);
+    p->packed64_f8.push_back(pw8s);
     p->w32.push_back(w32);
     p->w_n.push_back(N);
     p->w_k.push_back(K);

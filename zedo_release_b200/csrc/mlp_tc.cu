@@ -29,8 +29,9 @@ struct TileCfg {
   // NPROD = 3: A_hi.W_hi + A_lo.W_hi + A_hi.W_lo | 2: A_hi.W_hi + A_hi.W_lo | 1: A_hi.W_hi
   static constexpr int kAImage = kActTileRows * kBlockK * 2;  // bytes of one hi or lo A image (16 KiB)
   static constexpr int kBImage = BN * kBlockK * 2;
-  static constexpr int kABytes = kAImage * (NPROD == 3 ? 2 : 1);
-  static constexpr int kBBytes = kBImage * (NPROD >= 2 ? 2 : 1);
+  // NPROD = 4 (ZEDO_GEMM_FP8LO): stages hold the [hi16 | hi8 | lo8] images of both operands, see mlp_tc2.cu
+  static constexpr int kABytes = NPROD == 4 ? 2 * kAImage : kAImage * (NPROD == 3 ? 2 : 1);
+  static constexpr int kBBytes = NPROD == 4 ? 2 * kBImage : kBImage * (NPROD >= 2 ? 2 : 1);
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kMaxStages = (225 * 1024) / kStageBytes;
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
@@ -146,12 +147,23 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) layer_tc_kernel(const Layer
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
             umma_f16(d_tmem, a_hi + kAStep * k, b_hi + kBStep * k, idesc, (kb | k) != 0);
+          if (NPROD == 4) {
+            // the two low-order products in e4m3, same order as the CTA-pair kernel (bit-identical results)
+            const uint64_t a_hi8 = make_kmajor_desc(a_addr + Cfg::kAImage, kActTileRows);
+            const uint64_t a_lo8 = make_kmajor_desc(a_addr + Cfg::kAImage + Cfg::kAImage / 2, kActTileRows);
+            const uint64_t b_hi8 = make_kmajor_desc(b_addr + Cfg::kBImage, BN);
+            const uint64_t b_lo8 = make_kmajor_desc(b_addr + Cfg::kBImage + Cfg::kBImage / 2, BN);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 32; ++k) umma_f8(d_tmem, a_lo8 + kAStep * k, b_hi8 + kBStep * k, idesc, 1);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 32; ++k) umma_f8(d_tmem, a_hi8 + kAStep * k, b_lo8 + kBStep * k, idesc, 1);
+          }
           if (NPROD == 3) {
             const uint64_t a_lo = make_kmajor_desc(a_addr + Cfg::kAImage, kActTileRows);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k) umma_f16(d_tmem, a_lo + kAStep * k, b_hi + kBStep * k, idesc, 1);
           }
-          if (NPROD >= 2) {
+          if (NPROD == 2 || NPROD == 3) {
             const uint64_t b_lo = make_kmajor_desc(b_addr + Cfg::kBImage, BN);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k) umma_f16(d_tmem, a_hi + kAStep * k, b_lo + kBStep * k, idesc, 1);
@@ -228,11 +240,17 @@ static int launch_nprod(const LayerArgs& a, int nprod, int num_sms, cudaStream_t
   }
 }
 
-// bn: 256 (hidden layers) or 64 (post_dense); nprod: 3 / 2 / 1 MMA passes; epi: EPI_*
+// bn: 256 (hidden layers) or 64 (post_dense); nprod: 3 / 2 / 1 MMA passes, 4 = fp8lo (64-channel tiles only); epi: EPI_*
 int launch_layer_tc(const LayerArgs& a_in, int bn, int nprod, int epi, int num_sms, cudaStream_t st) {
   static const int dbg = getenv("ZEDO_DBG") ? atoi(getenv("ZEDO_DBG")) : 0;
   LayerArgs a = a_in;
   a.dbg = dbg;
+  if (nprod == 4) {  // small-batch form of the fp8lo layers: format-1 A blocks, [hi16 | hi8 | lo8] weight tiles
+    if (bn != 64 || a.a_fmt != 1) return ZEDO_E_INVALID;
+    if (epi == EPI_GN_SILU) return launch_ew<64, 4, EPI_GN_SILU, 8>(a, num_sms, st);
+    if (epi == EPI_LINEAR_ACT) return launch_ew<64, 4, EPI_LINEAR_ACT, 8>(a, num_sms, st);
+    return ZEDO_E_INVALID;
+  }
   if (bn == 256 && epi == EPI_GN_SILU) return launch_nprod<256, EPI_GN_SILU>(a, nprod, num_sms, st);
   if (bn == 256 && epi == EPI_LINEAR_ACT) return launch_nprod<256, EPI_LINEAR_ACT>(a, nprod, num_sms, st);
   if (bn == 64 && epi == EPI_LINEAR_F32) return launch_nprod<64, EPI_LINEAR_F32>(a, nprod, num_sms, st);
