@@ -161,6 +161,8 @@ struct zedo_plan {
   int small_batch_tiles = 18;             // use the 64-wide tiles when the batch has at most this many 128-row tiles
   std::vector<GemmOp> program;
   bool use_pairs = true;
+  bool f8_ok = true;      // every 1024 x 1024 weight has max/rms <= 16 (or ZEDO_FP8LO_FORCE=1)
+  bool f8_force = false;
 
   // workspaces
   __half* xa = nullptr;            // [m_pad, 64] blocked hi/lo
@@ -401,9 +403,10 @@ int net_forward(zedo_plan* p, const float* x, const float* tbl, int64_t B, int m
   // 64-channel tiles of the one-CTA kernel for small batches: same products, same order, so a pose's result does not
   // depend on the batch it travels in); the K = 64 first layer and post_dense keep the three fp16 products and only
   // read / write the format-1 blocks.
-  const bool f8 = mode == ZEDO_GEMM_FP8LO;
+  // a plan whose hidden weights are too heavy-tailed for the e4m3 images runs FP8LO requests as SPLIT3 (f8_ok)
+  const bool f8 = mode == ZEDO_GEMM_FP8LO && p->f8_ok;
   if (f8 && !p->use_pairs) return ZEDO_E_INVALID;
-  const int nprod = (mode == ZEDO_GEMM_SPLIT3 || f8) ? 3 : (mode == ZEDO_GEMM_SPLIT2 ? 2 : 1);
+  const int nprod = (mode == ZEDO_GEMM_SPLIT3 || mode == ZEDO_GEMM_FP8LO) ? 3 : (mode == ZEDO_GEMM_SPLIT2 ? 2 : 1);
   if (!xa_ready && (rc = launch_pack_x(x, p->xa, B, p->D, st))) return rc;
   for (const GemmOp& op : p->program) {
     const PackedWeight& w = p->packed[op.weight];
@@ -523,6 +526,7 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
   p->cap = max_batch;
   p->m_pad = round_up(max_batch, 2 * kActTileRows);  // CTA pairs work on 256 rows
   p->use_pairs = !(getenv("ZEDO_TC2") && atoi(getenv("ZEDO_TC2")) == 0);
+  p->f8_force = getenv("ZEDO_FP8LO_FORCE") && atoi(getenv("ZEDO_FP8LO_FORCE")) != 0;
   if (getenv("ZEDO_SMALL_TILES")) p->small_batch_tiles = atoi(getenv("ZEDO_SMALL_TILES"));
   int rc = 0;
 #define PLAN_TRY(expr)         \
@@ -570,6 +574,16 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
     }
     p->packed64.push_back(pw64);
     if (K == H && N == H) {
+      // FP8LO keeps e4m3(W_hi * 2^-11) under ONE power-of-two scale per matrix: entries more than ~16x below the
+      // maximum fall into the e4m3 subnormals and the mode degrades towards split2 accuracy.  Typical
+      // entries are judged by the rms; uniform / Gaussian initialisations and trained checkpoints sit at 2-6.
+      double sq = 0.0, mx = 0.0;
+      for (float v : *w) {
+        sq += (double)v * v;
+        mx = std::fmax(mx, std::fabs((double)v));
+      }
+      const double rms = std::sqrt(sq / (double)w->size());
+      if (!(rms > 0.0) || mx / rms > 16.0) p->f8_ok = p->f8_force;
       if ((r = pack_weight(w->data(), N, K, 128, &pw2))) return r > 0 ? -1000 - r : r;
       p->owned.push_back(pw2.dev);
       if ((r = pack_weight_f8(w->data(), N, K, 128, &pw8))) return r > 0 ? -1000 - r : r;
