@@ -157,3 +157,25 @@ def test_gather_rows_world2_gloo(built_lib, tmp_path, n):
         port = s.getsockname()[1]
     mp.spawn(_gloo_worker, args=(2, port, n, str(tmp_path)), nprocs=2, join=True)
     assert [open(tmp_path / f"rank{r}.txt").read() for r in range(2)] == ["ok", "ok"]
+
+
+def test_e4m3_emulator_known_answers():
+    """tools/precision_study.py emulates the e4m3 operands of the fp8lo GEMM mode on the CPU (the study the mode was
+    built on): round-to-nearest-even on 4 significant bits, min normal 2^-6, subnormal step 2^-9, saturation at 448."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("precision_study", os.path.join(ROOT, "tools", "precision_study.py"))
+    ps = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ps)
+    x = np.array([0.0, 1.0, -1.0, 0.3, 300.0, 500.0, -1000.0, 448.0, 1.0625, 1.1875, 2.0 ** -6, 0.001, 0.0009,
+                  2.0 ** -9, 3 * 2.0 ** -10], dtype=np.float32)
+    want = np.array([0.0, 1.0, -1.0, 0.3125, 288.0, 448.0, -448.0, 448.0, 1.0, 1.25, 2.0 ** -6, 2.0 ** -9, 0.0,
+                     2.0 ** -9, 2.0 ** -8], dtype=np.float32)
+    assert np.array_equal(ps.e4m3(x), want)
+    # every value the emulator returns is on the e4m3 grid: idempotent
+    r = np.random.default_rng(0).normal(0, 30, 10000).astype(np.float32)
+    q = ps.e4m3(r)
+    assert np.array_equal(ps.e4m3(q), q) and np.abs(q).max() <= 448
+    # and the three-product split it models: hi16 + lo16 reproduces a float32 activation to ~2^-22
+    a = r / 30
+    hi = ps.fp16(a)
+    assert np.abs(a - (hi + ps.fp16(a - hi))).max() <= 2.0 ** -21 * np.abs(a).max()

@@ -23,9 +23,6 @@ import numpy as np
 import zedo_oracle as zo
 
 f32 = np.float32
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
-DAMP = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
 
 
 def fp16(x):
@@ -100,6 +97,9 @@ def make_forward(W, mode):
 
 
 def main():
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+    STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+    DAMP = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
     W = zo.make_weights(seed=0)
     if DAMP != 1.0:  # realistic-scale network output (tests/golden/oil_small.npz uses 0.05)
         W["post_dense.weight"] = (W["post_dense.weight"] * f32(DAMP)).astype(f32)
