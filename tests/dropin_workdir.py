@@ -1,0 +1,57 @@
+"""A working directory the reference's own driver (run/opt_main.py) can run in: synthetic H36M-format
+``data/h36m/h36m_test.pkl`` (+ detections), ``clusters/h36m_cluster{S}.npy``, a checkpoint in the reference's
+format and a config FILE in the reference's format (its get_config() starts from the shipped
+``configs/optim/concat_pose_optimization_h36m.py`` and only changes sizes / iteration counts)."""
+import os
+import pickle
+
+import numpy as np
+
+CONFIG_TEMPLATE = '''\
+from configs.optim.concat_pose_optimization_h36m import get_config as _shipped
+
+
+def get_config():
+    config = _shipped()
+    config.ZeDO.sample = 1
+    config.ZeDO.batch = {batch}
+    config.ZeDO.IPO_iterations = {ipo}
+    config.ZeDO.OIL_iterations = {oil}
+    return config
+'''
+
+
+def make_workdir(path, n_poses=64, hypo=2, ipo=10, oil=100, seed=1234):
+    import torch
+    from zedo_release_b200 import synthetic as sy
+    ds = sy.make_synthetic_dataset(n_poses, seed=seed, n_clusters=hypo)
+    os.makedirs(os.path.join(path, "data", "h36m"), exist_ok=True)
+    os.makedirs(os.path.join(path, "clusters"), exist_ok=True)
+    os.makedirs(os.path.join(path, "ckpt"), exist_ok=True)
+    with open(os.path.join(path, "data", "h36m", "h36m_test.pkl"), "wb") as f:
+        pickle.dump(sy.h36m_items_from_arrays(ds), f)
+    det = {"test": {"joint3d_image": np.concatenate([ds["db_2d"][:, :, :2], np.zeros((n_poses, 17, 1), np.float32)], -1),
+                    "confidence": ds["db_2d"][:, :, 2:3].copy()}}
+    with open(os.path.join(path, "data", "h36m", "h36m_sh_dt_ft.pkl"), "wb") as f:
+        pickle.dump(det, f)
+    np.save(os.path.join(path, "clusters", f"h36m_cluster{hypo}.npy"), ds["clusters"].astype(np.float32))
+    W = sy.make_weights(seed=0)
+    sd = {"module." + k: torch.tensor(v) for k, v in W.items()}
+    sd["module.sigmas"] = torch.tensor(np.exp(np.linspace(np.log(50), np.log(0.01), 1000)))
+    shadow = [torch.tensor(v) for k, v in W.items()]
+    torch.save({"model_state_dict": sd, "ema": {"decay": 0.9999, "num_updates": 7, "shadow_params": shadow},
+                "step": 1500}, os.path.join(path, "ckpt", "checkpoint_1500.pth"))
+    cfg = os.path.join(path, "zedo_test_config.py")
+    with open(cfg, "w") as f:
+        f.write(CONFIG_TEMPLATE.format(batch=n_poses, ipo=ipo, oil=oil))
+    return dict(config=cfg, ckpt_dir=os.path.join(path, "ckpt"), ckpt_name="checkpoint_1500.pth", ds=ds)
+
+
+def parse_table(stdout):
+    """The 'p1' / 'p2' rows run/opt_main.py prints through eval_multi(print_verbose=True): -> {'p1': [...], 'p2': [...]}."""
+    out = {}
+    for line in stdout.splitlines():
+        cells = [c.strip() for c in line.strip().strip("|").split("|")]
+        if cells and cells[0] in ("p1", "p2") and len(cells) == 17:
+            out[cells[0]] = [float(c) for c in cells[1:]]
+    return out
