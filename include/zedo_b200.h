@@ -11,6 +11,10 @@
  *     own layouts unless a parameter is marked "host".
  *   - All work is enqueued on the caller's stream (cudaStream_t passed as void*; NULL =
  *     legacy default stream); no hidden synchronisation except where noted.
+ *   - No device allocation after set-up: zedo_plan_create sizes the workspaces for max_batch and
+ *     zedo_plan_reserve the per-step bias tables for the longest schedule; only a call that exceeds what
+ *     was reserved grows a buffer (stream-ordered, with one stream synchronisation).  Index lists
+ *     (keylist, joint_subset) travel in the kernel parameters.
  *   - Return value: 0 = OK, <0 = ZEDO_E_* argument error, >0 = cudaError_t.  Never throws.
  *   - A plan is bound to one device and one stream at a time and is not thread-safe
  *     (one plan per process/GPU, matching one-process-per-GPU sharding).
@@ -26,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ZEDO_B200_ABI_VERSION 1
+#define ZEDO_B200_ABI_VERSION 2
 
 /* argument errors */
 #define ZEDO_E_INVALID   (-1)  /* NULL pointer / bad enum */
@@ -75,6 +79,24 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
                      const int64_t* numels, int64_t max_batch, int32_t device);
 int zedo_plan_destroy(zedo_plan* plan);
 int64_t zedo_plan_capacity(const zedo_plan* plan);
+/* Size the per-step bias tables for schedules of up to max_steps steps (config.ZeDO.OIL_iterations,
+ * run/opt_main.py:197) and, for gemm_mode == ZEDO_GEMM_FP32, the float32 validation workspaces, so that no
+ * later call allocates.  Synchronises `stream`. */
+int zedo_plan_reserve(zedo_plan* plan, int32_t max_steps, int32_t gemm_mode, void* stream);
+
+/* ---- process-wide tuning options ---------------------------------------------------------------
+ * Defaults are the product path; none selects a non-CUDA path.  Initial values may be given through the
+ * environment variable named beside each option (read once, at first use). */
+#define ZEDO_OPT_GEOM_KERNEL     0  /* geometry kernel: 0 = by batch size, 1 = warp per pose, 2 = 128-pose CTAs (ZEDO_GEOM) */
+#define ZEDO_OPT_PDL             1  /* programmatic dependent launch between the kernels of a step (ZEDO_PDL), default 1 */
+#define ZEDO_OPT_SMALL_TILES     2  /* batches of at most this many 128-row tiles use 64-channel tiles (ZEDO_SMALL_TILES), 18;
+                                       read by zedo_plan_create */
+#define ZEDO_OPT_CTA_PAIRS       3  /* cta_group::2 kernel for the 1024x1024 layers (ZEDO_TC2), default 1; read by plan_create */
+#define ZEDO_OPT_FP8LO_FORCE     4  /* e4m3 low-order products even for heavy-tailed weights (ZEDO_FP8LO_FORCE), default 0 */
+#define ZEDO_OPT_EXPERIMENT      5  /* timing experiments; only in builds with -DZEDO_EXPERIMENTS=1 (ZEDO_DBG) */
+#define ZEDO_OPT_COUNT           6
+int zedo_set_option(int32_t option, int32_t value);
+int zedo_get_option(int32_t option, int32_t* value);
 
 /* ---- score network forward -----------------------------------------------------------------
  * Replaces: ScoreModelFC_Adv.forward(batch, t, condition, mask) (model.py:215-298) in eval
@@ -111,7 +133,7 @@ int zedo_sde_step(zedo_plan* plan, const float* x, float t, const float* z, int3
  * T [B,3] in/out, t_sched host float[steps] (= torch.linspace(sde.T, eps, steps)).
  * Steps i < phase_switch keep T; later steps re-solve it (phase_switch = steps/5 in
  * opt_main.py:203, 950 in opt_main_infant.py:310).  dump (nullable) [n_dump,B,J,3] receives
- * the pose after step dump_steps[k] (host int array, ascending). */
+ * the pose after step dump_steps[k] (host int array, strictly ascending). */
 int zedo_oil_loop(zedo_plan* plan, float* x, float* T, const float* uv, const float* K,
                   float* conf, const float* t_sched, int32_t steps, int32_t phase_switch,
                   float beta_min, float beta_max, int32_t n_scales, float* dump,

@@ -23,7 +23,7 @@ def test_header_symbols_exported(built_lib):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/zedo_b200.h but not exported"
     assert set(syms) == set(built_lib.EXPORTS)
-    assert built_lib.lib.zedo_abi_version() == 1
+    assert built_lib.lib.zedo_abi_version() == 2
 
 
 def test_strerror_and_argument_errors(built_lib):
@@ -78,3 +78,25 @@ def test_mode_constants_match_the_header(built_lib):
         assert defs[f"ZEDO_GEMM_{name.upper()}"] == value
     assert sorted(engine.GEMM_MODES.values()) == sorted(v for k, v in defs.items() if k.startswith("ZEDO_GEMM_"))
     assert defs["ZEDO_NET_SCORE_FC_ADV"] == built_lib.NET_SCORE_FC_ADV and defs["ZEDO_NET_CONTROL"] == built_lib.NET_CONTROL
+
+
+def test_options_and_argument_validation(built_lib):
+    """zedo_set_option / zedo_get_option round trip; entry points validate sizes instead of throwing across the ABI."""
+    nat = built_lib
+    assert nat.get_option(nat.OPT_GEOM_KERNEL) == 0 and nat.get_option(nat.OPT_PDL) == 1
+    nat.set_option(nat.OPT_GEOM_KERNEL, 2)
+    assert nat.get_option(nat.OPT_GEOM_KERNEL) == 2
+    nat.set_option(nat.OPT_GEOM_KERNEL, 0)
+    assert nat.lib.zedo_set_option(99, 1) == -1
+    assert nat.lib.zedo_set_option(nat.OPT_EXPERIMENT, 1) == -5  # timing experiments are not in the shipped build
+    # negative / absurd element counts are argument errors, not std::length_error through ctypes
+    desc = nat.NetDesc(nat.NET_SCORE_FC_ADV, 17, 1024, 512, 2, 1e-5)
+    h = ctypes.c_void_p()
+    names = (ctypes.c_char_p * 1)(b"pre_dense.weight")
+    buf = (ctypes.c_float * 4)()
+    ptrs = (ctypes.c_void_p * 1)(ctypes.addressof(buf))
+    for bad in (-1, 1 << 40):
+        rc = nat.lib.zedo_plan_create(ctypes.byref(h), ctypes.byref(desc), 1, names, ptrs, (ctypes.c_int64 * 1)(bad), 8, 0)
+        assert rc == -1 and not h.value
+    assert nat.lib.zedo_plan_create(ctypes.byref(h), ctypes.byref(desc), -3, names, ptrs, (ctypes.c_int64 * 1)(4), 8, 0) == -1
+    assert nat.lib.zedo_plan_reserve(None, 1000, 0, None) == -1

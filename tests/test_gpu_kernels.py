@@ -38,11 +38,12 @@ def plan17(zr):
 
 # ---- geometry (K3) ---------------------------------------------------------------------------------
 @pytest.fixture(params=["warp", "block"])
-def geom_kernel(request, monkeypatch):
+def geom_kernel(request, built_lib):
     """Both geometry kernels (csrc/geom.cu: warp per pose for small batches, 128 poses per CTA once the batch
-    fills the GPU) behind the same entry point."""
-    monkeypatch.setenv("ZEDO_GEOM", request.param)
-    return request.param
+    fills the GPU) behind the same entry point (zedo_set_option(ZEDO_OPT_GEOM_KERNEL))."""
+    built_lib.set_option(built_lib.OPT_GEOM_KERNEL, {"warp": 1, "block": 2}[request.param])
+    yield request.param
+    built_lib.set_option(built_lib.OPT_GEOM_KERNEL, 0)
 
 
 @pytest.mark.parametrize("tag,use_t,use_conf", [("fixedT_conf", True, True), ("solveT_conf", False, True),
@@ -104,13 +105,14 @@ def test_geometry_kernels_agree_bitwise(zr, monkeypatch, J, B):
     plan = zr.ScorePlan(W, n_joints=J, max_batch=B)
     out = {}
     for poses in ("warp", "block"):
-        monkeypatch.setenv("ZEDO_GEOM", poses)
+        zr._native.set_option(zr._native.OPT_GEOM_KERNEL, {"warp": 1, "block": 2}[poses])
         g, T = zr.grad_field(dev(uv), dev(x0), dev(K), conf=dev(conf))
         x, Tl = dev(x0), dev(zo.init_translation(uv, K, 3.0).reshape(B, 3))
         dump = plan.oil_loop(x, Tl, dev(uv), dev(K), dev(conf), zo.oil_time_grid()[500:504], phase_switch=2,
                              dump_steps=range(4), mode="split3")
         out[poses] = (g, T, x, Tl, dump)
     plan.close()
+    zr._native.set_option(zr._native.OPT_GEOM_KERNEL, 0)
     for a, b in zip(out["warp"], out["block"]):
         assert torch.equal(a, b)
 
@@ -637,3 +639,53 @@ def test_multi_hypothesis_selection_matches_oracle(zr, plan17):
         assert np.abs(e.cpu().numpy() - res_o).max() < (2e-7 if p2 else 1e-12)
         assert abs(zr.aggregate_errors(e, ds["actions"]) - agg_o) < 2e-7
     assert len(set(idx.cpu().numpy().tolist())) > 1  # different poses pick different hypotheses
+
+
+# ---- boundary hygiene: caller's stream, reservation, duplicate dump requests ------------------------------------
+def test_oil_loop_on_a_side_stream_with_table_growth(zr):
+    """The first 1000-step call grows the per-step bias tables; everything it does (allocation zeroing, table build,
+    loop) is ordered on the CALLER's stream, so a non-blocking side stream sees the same result as the default
+    stream, and a reserved plan never grows at all."""
+    B = 300
+    ds = zo.make_synthetic_dataset(B, seed=5)
+    W = zo.make_weights(seed=0)
+    uv, K, conf = dev(ds["db_2d"][:, :, :2]), dev(ds["camera_param"]), dev(ds["db_2d"][:, :, 2])
+    x0 = dev(ds["db_3d"] + 0.05)
+    T0 = dev(zo.init_translation(ds["db_2d"][:, :, :2], ds["camera_param"], 3.0).reshape(B, 3))
+    ts = zo.oil_time_grid()[:200]
+    results = []
+    for reserve, side in ((False, True), (True, True), (False, False)):
+        plan = zr.ScorePlan(W, n_joints=17, max_batch=B, device=0)
+        if reserve:
+            plan.reserve(1000)
+        x, T = x0.clone(), T0.clone()
+        torch.cuda.synchronize()
+        if side:
+            s = torch.cuda.Stream()  # non-blocking: not ordered against the legacy default stream
+            with torch.cuda.stream(s):
+                plan.oil_loop(x, T, uv, K, conf.clone(), ts, phase_switch=40)
+            s.synchronize()
+        else:
+            plan.oil_loop(x, T, uv, K, conf.clone(), ts, phase_switch=40)
+            torch.cuda.synchronize()
+        results.append((x.clone(), T.clone()))
+        plan.close()
+    for x, T in results[1:]:
+        assert torch.equal(x, results[0][0]) and torch.equal(T, results[0][1])
+    assert bool(torch.isfinite(results[0][0]).all())
+
+
+def test_duplicate_dump_steps_are_served(zr, plan17, golden):
+    g, geo, x_rot = _oil_inputs(golden)
+    uv, K, conf = geo["db_2d"][:, :, :2], geo["K"], geo["db_2d"][:, :, 2]
+    ts = zo.oil_time_grid()[:6]
+    x, T = dev(x_rot), dev(g["T"].reshape(16, 3))
+    d = plan17.oil_loop(x, T, dev(uv), dev(K), dev(conf), ts, phase_switch=2, dump_steps=[3, 1, 3, 5])
+    assert d.shape[0] == 4 and torch.equal(d[1], d[2]) and torch.equal(d[3], x) and not torch.equal(d[0], d[1])
+    # the C ABI itself rejects non-strictly-ascending lists
+    import ctypes as C
+    nat = zr._native
+    rc = nat.lib.zedo_oil_loop(plan17._h, C.c_void_p(x.data_ptr()), C.c_void_p(T.data_ptr()), C.c_void_p(dev(uv).data_ptr()),
+                               C.c_void_p(dev(K).data_ptr()), None, nat.f32_array(ts), 6, 2, 0.1, 20.0, 1000,
+                               C.c_void_p(d.data_ptr()), nat.i32_array([1, 1]), 2, 16, 0, None)
+    assert rc == -1

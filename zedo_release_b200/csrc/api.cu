@@ -6,7 +6,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <new>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -16,9 +18,47 @@
 
 namespace zedo {
 
-bool pdl_enabled() {
-  static const bool on = !(getenv("ZEDO_PDL") && atoi(getenv("ZEDO_PDL")) == 0);
-  return on;
+// ---- process-wide options (zedo_set_option) ------------------------------------------------------------
+namespace {
+struct Options {
+  std::atomic<int> v[ZEDO_OPT_COUNT];
+  Options() {
+    const int defaults[ZEDO_OPT_COUNT] = {/*GEOM_KERNEL*/ 0, /*PDL*/ 1, /*SMALL_TILES*/ 18, /*CTA_PAIRS*/ 1,
+                                          /*FP8LO_FORCE*/ 0, /*EXPERIMENT*/ 0};
+    const char* env[ZEDO_OPT_COUNT] = {"ZEDO_GEOM", "ZEDO_PDL", "ZEDO_SMALL_TILES", "ZEDO_TC2", "ZEDO_FP8LO_FORCE",
+                                       "ZEDO_DBG"};
+    for (int i = 0; i < ZEDO_OPT_COUNT; ++i) {
+      int val = defaults[i];
+      if (const char* e = getenv(env[i])) {  // read once, here; never on a launch path
+        if (i == ZEDO_OPT_GEOM_KERNEL)
+          val = strcmp(e, "warp") == 0 ? 1 : (strcmp(e, "block") == 0 ? 2 : atoi(e));
+        else
+          val = atoi(e);
+      }
+      v[i].store(val, std::memory_order_relaxed);
+    }
+  }
+};
+Options& options() {
+  static Options o;
+  return o;
+}
+std::mutex g_smem_mu;
+std::set<std::pair<int, const void*>> g_smem_set;
+}  // namespace
+
+int option_get(int opt) { return options().v[opt].load(std::memory_order_relaxed); }
+bool pdl_enabled() { return option_get(ZEDO_OPT_PDL) != 0; }
+
+cudaError_t ensure_max_smem(const void* func, int bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(g_smem_mu);
+  if (g_smem_set.count({dev, func})) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) g_smem_set.insert({dev, func});
+  return e;
 }
 
 static std::atomic<int64_t> g_launches{0};
@@ -208,20 +248,16 @@ struct DeviceGuard {
   }
 };
 
-// a short host int array on the device for the duration of one launch (stream-ordered allocation)
-struct StreamInts {
-  int* dev = nullptr;
-  cudaStream_t st;
-  explicit StreamInts(cudaStream_t s) : st(s) {}
-  int put(const int32_t* host, int n) {
-    ZEDO_CUDA_TRY(cudaMallocAsync((void**)&dev, (size_t)n * sizeof(int), st));
-    ZEDO_CUDA_TRY(cudaMemcpyAsync(dev, host, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
-    return 0;
+// host index list -> by-value kernel parameter (no device allocation or copy per call)
+inline bool make_int_list(const int32_t* host, int n, int max_value, IntList* out) {
+  if (n < 0 || n > 32) return false;
+  out->n = n;
+  for (int i = 0; i < n; ++i) {
+    if (host[i] < 0 || host[i] >= max_value) return false;
+    out->v[i] = host[i];
   }
-  ~StreamInts() {
-    if (dev) cudaFreeAsync(dev, st);
-  }
-};
+  return true;
+}
 
 // brackets one launch with events when profiling is on and this launch is sampled
 struct ProfScope {
@@ -252,11 +288,33 @@ struct ProfScope {
 
 namespace {
 
+// plan construction only (zedo_plan_create ends with a device synchronisation)
 template <class T>
 int dev_alloc(zedo_plan* p, T** ptr, size_t count) {
   ZEDO_CUDA_TRY(cudaMalloc((void**)ptr, count * sizeof(T)));
   ZEDO_CUDA_TRY(cudaMemset(*ptr, 0, count * sizeof(T)));
   p->owned.push_back(*ptr);
+  return 0;
+}
+
+// growth after construction (a schedule longer than reserved, the first FP32-mode call): the buffer is zeroed ON
+// THE CALLER'S STREAM -- a legacy-stream memset would not be ordered against a non-blocking stream -- and the buffer
+// it replaces is released once that stream has drained.  zedo_plan_reserve moves all of this to set-up time.
+template <class T>
+int dev_regrow(zedo_plan* p, T** ptr, size_t count, cudaStream_t st) {
+  if (*ptr != nullptr) {
+    ZEDO_CUDA_TRY(cudaStreamSynchronize(st));
+    for (auto it = p->owned.begin(); it != p->owned.end(); ++it)
+      if (*it == (void*)*ptr) {
+        p->owned.erase(it);
+        break;
+      }
+    ZEDO_CUDA_TRY(cudaFree(*ptr));
+    *ptr = nullptr;
+  }
+  ZEDO_CUDA_TRY(cudaMalloc((void**)ptr, count * sizeof(T)));
+  p->owned.push_back(*ptr);
+  ZEDO_CUDA_TRY(cudaMemsetAsync(*ptr, 0, count * sizeof(T), st));
   return 0;
 }
 
@@ -276,18 +334,17 @@ struct TensorMap {
   }
 };
 
-int ensure_tables(zedo_plan* p, int steps) {
+int ensure_tables(zedo_plan* p, int steps, cudaStream_t st) {
   if (steps <= p->table_steps) return 0;
-  // old buffers stay owned by the plan until destroy; schedules are rarely re-grown
   int rc;
-  if ((rc = dev_alloc(p, &p->t999_dev, (size_t)steps))) return rc;
-  if ((rc = dev_alloc(p, &p->emb, (size_t)steps * p->E))) return rc;
-  if ((rc = dev_alloc(p, &p->temb, (size_t)steps * p->E))) return rc;
-  if ((rc = dev_alloc(p, &p->table, (size_t)steps * p->L * p->H))) return rc;
+  if ((rc = dev_regrow(p, &p->t999_dev, (size_t)steps, st))) return rc;
+  if ((rc = dev_regrow(p, &p->emb, (size_t)steps * p->E, st))) return rc;
+  if ((rc = dev_regrow(p, &p->temb, (size_t)steps * p->E, st))) return rc;
+  if ((rc = dev_regrow(p, &p->table, (size_t)steps * p->L * p->H, st))) return rc;
   if (p->desc.kind == ZEDO_NET_CONTROL) {
-    if ((rc = dev_alloc(p, &p->proj, (size_t)steps * p->Lt * p->H))) return rc;
-    if ((rc = dev_alloc(p, &p->ubuf, (size_t)steps * p->H))) return rc;
-    if ((rc = dev_alloc(p, &p->sbuf, (size_t)steps * p->H))) return rc;
+    if ((rc = dev_regrow(p, &p->proj, (size_t)steps * p->Lt * p->H, st))) return rc;
+    if ((rc = dev_regrow(p, &p->ubuf, (size_t)steps * p->H, st))) return rc;
+    if ((rc = dev_regrow(p, &p->sbuf, (size_t)steps * p->H, st))) return rc;
   }
   p->table_steps = steps;
   return 0;
@@ -295,7 +352,7 @@ int ensure_tables(zedo_plan* p, int steps) {
 
 // table[s, l, :] = W_lt . SiLU(W_s emb(t999_s) + b_s) + b_lt + b_l      (model.py:253-259,265,273,281)
 int build_tables(zedo_plan* p, const float* t999_host, int steps, cudaStream_t st) {
-  int rc = ensure_tables(p, steps);
+  int rc = ensure_tables(p, steps, st);
   if (rc) return rc;
   std::vector<float> logt;
   if (p->fourier) {
@@ -355,11 +412,11 @@ int build_tables(zedo_plan* p, const float* t999_host, int steps, cudaStream_t s
   return 0;
 }
 
-int ensure_act32(zedo_plan* p) {
+int ensure_act32(zedo_plan* p, cudaStream_t st) {
   if (!p->act32.empty()) return 0;
   for (int i = 0; i < p->n_act + 1; ++i) {  // last one = raw GEMM output scratch
     float* b = nullptr;
-    int rc = dev_alloc(p, &b, (size_t)p->m_pad * p->H);
+    int rc = dev_regrow(p, &b, (size_t)p->m_pad * p->H, st);
     if (rc) return rc;
     p->act32.push_back(b);
   }
@@ -374,7 +431,7 @@ int net_forward(zedo_plan* p, const float* x, const float* tbl, int64_t B, int m
   int rc;
   const int m_tiles = (int)((B + kActTileRows - 1) / kActTileRows);
   if (mode == ZEDO_GEMM_FP32) {
-    if ((rc = ensure_act32(p))) return rc;
+    if ((rc = ensure_act32(p, st))) return rc;
     for (const GemmOp& op : p->program) {
       const float* in = op.in_buf < 0 ? x : p->act32[op.in_buf];
       const int K = p->w_k[op.weight], N = p->w_n[op.weight];
@@ -503,10 +560,15 @@ int64_t zedo_blocked_offset(int64_t row, int64_t col, int64_t cols, int32_t tile
 
 int64_t zedo_plan_capacity(const zedo_plan* plan) { return plan ? plan->cap : 0; }
 
-int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tensors, const char* const* names,
-                     const float* const* tensors, const int64_t* numels, int64_t max_batch, int32_t device) {
+static int plan_create_impl(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tensors, const char* const* names,
+                            const float* const* tensors, const int64_t* numels, int64_t max_batch, int32_t device,
+                            zedo_plan** partial) {
   if (!out || !desc || !names || !tensors || !numels) return ZEDO_E_INVALID;
   *out = nullptr;
+  if (n_tensors < 0 || n_tensors > 4096) return ZEDO_E_INVALID;
+  for (int i = 0; i < n_tensors; ++i)
+    if (numels[i] < 0 || numels[i] > ((int64_t)1 << 28) || (numels[i] > 0 && tensors[i] == nullptr))
+      return ZEDO_E_INVALID;  // the largest tensor of either network has 2^20 entries
   if (desc->kind != ZEDO_NET_SCORE_FC_ADV && desc->kind != ZEDO_NET_CONTROL) return ZEDO_E_INVALID;
   const int D = desc->n_joints * 3, H = desc->hidden, E = desc->embed, NB = desc->n_blocks;
   // GroupNorm(32, hidden): the fused epilogue normalises groups of exactly 32 contiguous channels,
@@ -518,6 +580,7 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
   if (on_device.err != cudaSuccess) return (int)on_device.err;
   zedo_plan* p = new (std::nothrow) zedo_plan();
   if (!p) return ZEDO_E_NOMEM;
+  *partial = p;  // the guard in zedo_plan_create destroys it if a C++ exception escapes
   p->desc = *desc;
   p->device = device;
   p->D = D;
@@ -525,14 +588,15 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
   p->E = E;
   p->cap = max_batch;
   p->m_pad = round_up(max_batch, 2 * kActTileRows);  // CTA pairs work on 256 rows
-  p->use_pairs = !(getenv("ZEDO_TC2") && atoi(getenv("ZEDO_TC2")) == 0);
-  p->f8_force = getenv("ZEDO_FP8LO_FORCE") && atoi(getenv("ZEDO_FP8LO_FORCE")) != 0;
-  if (getenv("ZEDO_SMALL_TILES")) p->small_batch_tiles = atoi(getenv("ZEDO_SMALL_TILES"));
+  p->use_pairs = option_get(ZEDO_OPT_CTA_PAIRS) != 0;
+  p->f8_force = option_get(ZEDO_OPT_FP8LO_FORCE) != 0;
+  p->small_batch_tiles = option_get(ZEDO_OPT_SMALL_TILES);
   int rc = 0;
 #define PLAN_TRY(expr)         \
   do {                         \
     rc = (expr);               \
     if (rc) {                  \
+      *partial = nullptr;      \
       zedo_plan_destroy(p);    \
       return rc;               \
     }                          \
@@ -771,13 +835,59 @@ int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tenso
   }
   PLAN_TRY(dev_alloc(p, &p->eps, (size_t)p->m_pad * 64));
   PLAN_TRY(dev_alloc(p, &p->x32, (size_t)p->m_pad * D));
-  PLAN_TRY(ensure_tables(p, 1));
+  PLAN_TRY(ensure_tables(p, 1, (cudaStream_t)0));
   PLAN_TRY((int)cudaDeviceSynchronize());
 #undef NEED
 #undef ADD_W
 #undef ADD_GN
 #undef PLAN_TRY
+  *partial = nullptr;
   *out = p;
+  return 0;
+}
+
+// The C ABI never throws: host allocations (std::vector / std::string / std::map) inside an entry point are caught
+// here and reported as ZEDO_E_NOMEM / ZEDO_E_INVALID.
+#define ZEDO_GUARDED(cleanup, ...)            \
+  try {                                       \
+    return __VA_ARGS__;                       \
+  } catch (const std::bad_alloc&) {           \
+    cleanup;                                  \
+    return ZEDO_E_NOMEM;                      \
+  } catch (...) {                             \
+    cleanup;                                  \
+    return ZEDO_E_INVALID;                    \
+  }
+
+int zedo_plan_create(zedo_plan** out, const zedo_net_desc* desc, int32_t n_tensors, const char* const* names,
+                     const float* const* tensors, const int64_t* numels, int64_t max_batch, int32_t device) {
+  zedo_plan* partial = nullptr;
+  ZEDO_GUARDED(zedo_plan_destroy(partial),
+               plan_create_impl(out, desc, n_tensors, names, tensors, numels, max_batch, device, &partial));
+}
+
+int zedo_set_option(int32_t option, int32_t value) {
+  if (option < 0 || option >= ZEDO_OPT_COUNT) return ZEDO_E_INVALID;
+  if (option == ZEDO_OPT_EXPERIMENT && !ZEDO_EXPERIMENTS && value != 0) return ZEDO_E_STATE;  // not in this build
+  options().v[option].store(value, std::memory_order_relaxed);
+  return 0;
+}
+
+int zedo_get_option(int32_t option, int32_t* value) {
+  if (option < 0 || option >= ZEDO_OPT_COUNT || !value) return ZEDO_E_INVALID;
+  *value = option_get(option);
+  return 0;
+}
+
+int zedo_plan_reserve(zedo_plan* plan, int32_t max_steps, int32_t gemm_mode, void* stream) {
+  if (!plan || max_steps < 1 || max_steps > (1 << 20)) return ZEDO_E_INVALID;
+  DeviceGuard on_device(plan->device);
+  if (on_device.err != cudaSuccess) return (int)on_device.err;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ensure_tables(plan, max_steps, st);
+  if (rc) return rc;
+  if (gemm_mode == ZEDO_GEMM_FP32 && (rc = ensure_act32(plan, st))) return rc;
+  ZEDO_CUDA_TRY(cudaStreamSynchronize(st));
   return 0;
 }
 
@@ -861,17 +971,17 @@ int zedo_sde_step(zedo_plan* plan, const float* x, float t, const float* z, int3
   return launch_sde_update(x, plan->eps, 64, z, c, predictor, probability_flow, x_next, x_mean, B, plan->D, st);
 }
 
-int zedo_oil_loop(zedo_plan* plan, float* x, float* T, const float* uv, const float* K, float* conf,
-                  const float* t_sched, int32_t steps, int32_t phase_switch, float beta_min, float beta_max,
-                  int32_t n_scales, float* dump, const int32_t* dump_steps, int32_t n_dump, int64_t B,
-                  int32_t gemm_mode, void* stream) {
+static int oil_loop_impl(zedo_plan* plan, float* x, float* T, const float* uv, const float* K, float* conf,
+                         const float* t_sched, int32_t steps, int32_t phase_switch, float beta_min, float beta_max,
+                         int32_t n_scales, float* dump, const int32_t* dump_steps, int32_t n_dump, int64_t B,
+                         int32_t gemm_mode, void* stream) {
   int rc = check_batch(plan, B);
   if (rc) return rc;
-  if (!x || !T || !uv || !K || !t_sched || steps < 0 || n_scales < 1) return ZEDO_E_INVALID;
+  if (!x || !T || !uv || !K || !t_sched || steps < 0 || steps > (1 << 20) || n_scales < 1) return ZEDO_E_INVALID;
   if (n_dump > 0 && (!dump || !dump_steps)) return ZEDO_E_INVALID;
   for (int k = 0; k < n_dump; ++k)
-    if (dump_steps[k] < 0 || dump_steps[k] >= steps || (k > 0 && dump_steps[k] < dump_steps[k - 1]))
-      return ZEDO_E_INVALID;  // ascending, inside the schedule
+    if (dump_steps[k] < 0 || dump_steps[k] >= steps || (k > 0 && dump_steps[k] <= dump_steps[k - 1]))
+      return ZEDO_E_INVALID;  // strictly ascending, inside the schedule
   if (B == 0 || steps == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int J = plan->desc.n_joints, D = plan->D;
@@ -890,7 +1000,6 @@ int zedo_oil_loop(zedo_plan* plan, float* x, float* T, const float* uv, const fl
     if (i > 0 && next_dump < n_dump && dump_steps[next_dump] == i - 1) {
       dump_ptr = dump + (size_t)next_dump * B * D;
       ++next_dump;
-      while (next_dump < n_dump && dump_steps[next_dump] == i - 1) ++next_dump;  // duplicates: first slot only
     }
     {
       // gradient_field_gen + `denoise_x += joint_gradient` (opt_main.py:203-208); conf is clamped in place by
@@ -916,6 +1025,14 @@ int zedo_oil_loop(zedo_plan* plan, float* x, float* T, const float* uv, const fl
   return 0;
 }
 
+int zedo_oil_loop(zedo_plan* plan, float* x, float* T, const float* uv, const float* K, float* conf,
+                  const float* t_sched, int32_t steps, int32_t phase_switch, float beta_min, float beta_max,
+                  int32_t n_scales, float* dump, const int32_t* dump_steps, int32_t n_dump, int64_t B,
+                  int32_t gemm_mode, void* stream) {
+  ZEDO_GUARDED((void)0, oil_loop_impl(plan, x, T, uv, K, conf, t_sched, steps, phase_switch, beta_min, beta_max,
+                                      n_scales, dump, dump_steps, n_dump, B, gemm_mode, stream));
+}
+
 int zedo_ipo_fit_ex(const float* x0, const float* uv, const float* K, const int32_t* keylist, int32_t nkey,
                     int32_t axes_mask, int32_t pelvis_a, int32_t pelvis_b, int32_t ray_init, float ipo_T, float minT,
                     float maxT, int32_t iters, int64_t B_global, float lr, float* R, float* T, float* x_rot, float* qs,
@@ -925,14 +1042,10 @@ int zedo_ipo_fit_ex(const float* x0, const float* uv, const float* K, const int3
   if (nkey < 1 || nkey > 32 || J < 1 || J > 64 || iters < 0 || iters > 4096 || B < 0 || B_global < 1 ||
       pelvis_a < 0 || pelvis_a >= J || pelvis_b < 0 || pelvis_b >= J)
     return ZEDO_E_SHAPE;
-  for (int i = 0; i < nkey; ++i)
-    if (keylist[i] < 0 || keylist[i] >= J) return ZEDO_E_SHAPE;
-  cudaStream_t st = (cudaStream_t)stream;
-  StreamInts kl(st);
-  int rc = kl.put(keylist, nkey);
-  if (rc) return rc;
-  return launch_ipo_fit(x0, uv, K, kl.dev, nkey, axes_mask, pelvis_a, pelvis_b, ray_init, ipo_T, minT, maxT, iters,
-                        B_global, lr, R, T, x_rot, qs, B, J, st);
+  IntList kl;
+  if (!make_int_list(keylist, nkey, J, &kl)) return ZEDO_E_SHAPE;
+  return launch_ipo_fit(x0, uv, K, kl, axes_mask, pelvis_a, pelvis_b, ray_init, ipo_T, minT, maxT, iters, B_global, lr,
+                        R, T, x_rot, qs, B, J, (cudaStream_t)stream);
 }
 
 int zedo_ipo_fit(const float* x0, const float* uv, const float* K, const int32_t* keylist, int32_t nkey,
@@ -964,13 +1077,10 @@ int zedo_eval_multi(const float* pred, const double* gt, int32_t protocol2, int6
   if (!pred || !gt || !err_min || !argmin) return ZEDO_E_INVALID;
   if (J < 1 || J > 32 || S < 1 || N < 0) return ZEDO_E_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
-  StreamInts sub(st);
-  if (joint_subset != nullptr) {
-    if (n_sub < 1 || n_sub > J) return ZEDO_E_SHAPE;
-    const int rc = sub.put(joint_subset, n_sub);
-    if (rc) return rc;
-  }
-  return launch_eval_multi(pred, gt, protocol2, N, S, J, sub.dev, n_sub, err_min, argmin, err_all, aligned, st);
+  IntList sub;
+  if (joint_subset != nullptr && (n_sub < 1 || n_sub > J || !make_int_list(joint_subset, n_sub, J, &sub)))
+    return ZEDO_E_SHAPE;
+  return launch_eval_multi(pred, gt, protocol2, N, S, J, sub, err_min, argmin, err_all, aligned, st);
 }
 
 int zedo_pck_counts(const float* pred, const double* gt, const int32_t* select, int64_t N, int32_t S, int32_t J,
@@ -979,14 +1089,11 @@ int zedo_pck_counts(const float* pred, const double* gt, const int32_t* select, 
   if (!pred || !gt || !counts) return ZEDO_E_INVALID;
   if (J < 1 || J > 32 || S < 1 || N < 0) return ZEDO_E_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
-  StreamInts sub(st);
-  if (joint_subset != nullptr) {
-    if (n_sub < 1 || n_sub > J) return ZEDO_E_SHAPE;
-    const int rc = sub.put(joint_subset, n_sub);
-    if (rc) return rc;
-  }
+  IntList sub;
+  if (joint_subset != nullptr && (n_sub < 1 || n_sub > J || !make_int_list(joint_subset, n_sub, J, &sub)))
+    return ZEDO_E_SHAPE;
   ZEDO_CUDA_TRY(cudaMemsetAsync(counts, 0, 31 * sizeof(uint64_t), st));
-  return launch_pck_counts(pred, gt, select, N, S, J, sub.dev, n_sub, (unsigned long long*)counts, st);
+  return launch_pck_counts(pred, gt, select, N, S, J, sub, (unsigned long long*)counts, st);
 }
 
 int zedo_hypothesis_std(const float* pred, int64_t N, int32_t S, int32_t J, double* out_std, void* stream) {

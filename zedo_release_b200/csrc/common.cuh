@@ -34,7 +34,19 @@ __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wa
 __device__ __forceinline__ void griddep_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
-bool pdl_enabled();  // env ZEDO_PDL (default on)
+bool pdl_enabled();  // option ZEDO_OPT_PDL (default on)
+
+// ---- process-wide tuning options (zedo_set_option; initial values may come from ZEDO_* environment variables,
+// read ONCE at first use -- never on a launch path) -------------------------------------------------------
+int option_get(int opt);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel) instead of on every launch
+cudaError_t ensure_max_smem(const void* func, int bytes);
+
+// Experiment code paths of the layer kernels (stale-stage / no-MMA timing runs) exist only in builds
+// with -DZEDO_EXPERIMENTS=1; the shipped library carries none of them.
+#ifndef ZEDO_EXPERIMENTS
+#define ZEDO_EXPERIMENTS 0
+#endif
 
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

@@ -51,7 +51,7 @@ __device__ void svd3x3_onesided(double* M, double* V) {
 
 __global__ void __launch_bounds__(128)
 eval_multi_kernel(const float* __restrict__ pred, const double* __restrict__ gt, int protocol2, int64_t N, int S,
-                  int J, const int* __restrict__ subset, int n_sub, double* __restrict__ err_min,
+                  int J, const IntList subset, double* __restrict__ err_min,
                   int* __restrict__ argmin, double* __restrict__ err_all, double* __restrict__ aligned) {
   const int lane = threadIdx.x & 31;
   const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -60,10 +60,10 @@ eval_multi_kernel(const float* __restrict__ pred, const double* __restrict__ gt,
   // joints that count in the mean: all J, or the listed subset (e.g. the 12 SyRIP joints)
   bool counted = active;
   int n_counted = J;
-  if (subset != nullptr) {
+  if (subset.n > 0) {
     counted = false;
-    for (int i = 0; i < n_sub; ++i) counted |= (subset[i] == lane);
-    n_counted = n_sub;
+    for (int i = 0; i < subset.n; ++i) counted |= (subset.v[i] == lane);
+    n_counted = subset.n;
   }
   double g0 = 0, g1 = 0, g2 = 0;
   if (active) {
@@ -143,7 +143,7 @@ eval_multi_kernel(const float* __restrict__ pred, const double* __restrict__ gt,
 // selected hypothesis against 31 thresholds linspace(0, 150, 31); counts[k] += #(error_mm < 5 k).
 __global__ void __launch_bounds__(128)
 pck_counts_kernel(const float* __restrict__ pred, const double* __restrict__ gt, const int* __restrict__ select,
-                  int64_t N, int S, int J, const int* __restrict__ subset, int n_sub,
+                  int64_t N, int S, int J, const IntList subset,
                   unsigned long long* __restrict__ counts) {
   __shared__ unsigned int local[31];
   if (threadIdx.x < 31) local[threadIdx.x] = 0;
@@ -152,9 +152,9 @@ pck_counts_kernel(const float* __restrict__ pred, const double* __restrict__ gt,
   const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n < N && lane < J) {
     bool counted = true;
-    if (subset != nullptr) {
+    if (subset.n > 0) {
       counted = false;
-      for (int i = 0; i < n_sub; ++i) counted |= (subset[i] == lane);
+      for (int i = 0; i < subset.n; ++i) counted |= (subset.v[i] == lane);
     }
     if (counted) {
       const int s = select != nullptr ? select[n] : 0;
@@ -171,11 +171,11 @@ pck_counts_kernel(const float* __restrict__ pred, const double* __restrict__ gt,
 }
 
 int launch_pck_counts(const float* pred, const double* gt, const int* select, int64_t N, int S, int J,
-                      const int* subset_dev, int n_sub, unsigned long long* counts, cudaStream_t st) {
+                      const IntList& subset, unsigned long long* counts, cudaStream_t st) {
   if (N == 0) return 0;
   const int warps = 4;
-  pck_counts_kernel<<<(unsigned)((N + warps - 1) / warps), warps * 32, 0, st>>>(pred, gt, select, N, S, J, subset_dev,
-                                                                             n_sub, counts);
+  pck_counts_kernel<<<(unsigned)((N + warps - 1) / warps), warps * 32, 0, st>>>(pred, gt, select, N, S, J, subset,
+                                                                             counts);
   ZEDO_LAUNCH_CHECK();
   return 0;
 }
@@ -210,12 +210,12 @@ int launch_hypothesis_std(const float* pred, int64_t N, int S, int J, double* ou
 }
 
 int launch_eval_multi(const float* pred, const double* gt, int protocol2, int64_t N, int S, int J,
-                      const int* subset_dev, int n_sub, double* err_min, int* argmin, double* err_all,
+                      const IntList& subset, double* err_min, int* argmin, double* err_all,
                       double* aligned, cudaStream_t st) {
   if (N == 0) return 0;
   const int warps = 4;
-  eval_multi_kernel<<<(unsigned)((N + warps - 1) / warps), warps * 32, 0, st>>>(pred, gt, protocol2, N, S, J, subset_dev,
-                                                                             n_sub, err_min, argmin, err_all, aligned);
+  eval_multi_kernel<<<(unsigned)((N + warps - 1) / warps), warps * 32, 0, st>>>(pred, gt, protocol2, N, S, J, subset,
+                                                                             err_min, argmin, err_all, aligned);
   ZEDO_LAUNCH_CHECK();
   return 0;
 }

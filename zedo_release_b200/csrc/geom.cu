@@ -504,15 +504,11 @@ int launch_grad_field(const float* uv, const float* x, const float* K, float* co
   } else {
     eps_prev = nullptr;
   }
-  // ZEDO_GEOM=warp|block forces one kernel (tests); default: 128-pose CTAs once the batch fills the GPU
-  const char* env = getenv("ZEDO_GEOM");
-  const int forced = env == nullptr ? 0 : (strcmp(env, "warp") == 0 ? 1 : (strcmp(env, "block") == 0 ? 2 : 0));
+  // ZEDO_OPT_GEOM_KERNEL forces one kernel (tests); default: 128-pose CTAs once the batch fills the GPU
+  const int forced = option_get(ZEDO_OPT_GEOM_KERNEL);
   if (forced == 2 || (forced == 0 && B >= kGeomBlockMinPoses)) {
     const size_t smem = (size_t)geom_smem_floats(J) * sizeof(float);
-    // per call, not cached: the attribute is per device and a process may drive several devices
-    if (smem > 48 * 1024)
-      ZEDO_CUDA_TRY(cudaFuncSetAttribute(grad_field_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem));
+    if (smem > 48 * 1024) ZEDO_CUDA_TRY(ensure_max_smem((const void*)grad_field_block_kernel, (int)smem));
     ZEDO_CUDA_TRY(launch_pdl(grad_field_block_kernel, dim3((unsigned)((B + kGeomPoses - 1) / kGeomPoses)),
                              dim3(kGeomThreads), smem, st, uv, x, K, conf, T, solve_T, clamp_inplace, g, x_out, xa, B,
                              J, eps_prev, nhb, g2, sd, dt, dump));

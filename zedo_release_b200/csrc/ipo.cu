@@ -99,11 +99,12 @@ __device__ __forceinline__ void adam_step(float& p, float g, float& m, float& v,
 
 __global__ void __launch_bounds__(kIpoThreads)
 ipo_fit_kernel(const float* __restrict__ x0, const float* __restrict__ uv, const float* __restrict__ Kmat,
-               const int* __restrict__ keylist, int nk, int axes_mask, int pelvis_a, int pelvis_b, int ray_init,
+               const IntList keylist, int axes_mask, int pelvis_a, int pelvis_b, int ray_init,
                float ipo_T, float minT, float maxT, int iters,
                float lam, float lr, float* __restrict__ Rout, float* __restrict__ Tout, float* __restrict__ x_rot,
                float* __restrict__ qs, int64_t B, int J) {
   extern __shared__ float sm[];
+  const int nk = keylist.n;
   float* step_size = sm;            // [iters]
   float* bc2_sqrt = sm + iters;     // [iters]
   float* sx = sm + 2 * iters;       // [nk][5][kIpoThreads]: X.x, X.y, X.z, u*, v*
@@ -118,7 +119,7 @@ ipo_fit_kernel(const float* __restrict__ x0, const float* __restrict__ uv, const
   const bool live = pose < B;
   const int64_t pc = live ? pose : 0;
   for (int k = 0; k < nk; ++k) {
-    const int j = keylist[k];
+    const int j = keylist.v[k];
     sx[(k * 5 + 0) * kIpoThreads + tid] = x0[(pc * J + j) * 3 + 0];
     sx[(k * 5 + 1) * kIpoThreads + tid] = x0[(pc * J + j) * 3 + 1];
     sx[(k * 5 + 2) * kIpoThreads + tid] = x0[(pc * J + j) * 3 + 2];
@@ -271,17 +272,17 @@ __global__ void rotopt_backward_kernel(const float* __restrict__ q, const float*
   d_scale[b] = ds;
 }
 
-int launch_ipo_fit(const float* x0, const float* uv, const float* K, const int* keylist_dev, int nk, int axes_mask,
+int launch_ipo_fit(const float* x0, const float* uv, const float* K, const IntList& keylist, int axes_mask,
                    int pelvis_a, int pelvis_b, int ray_init, float ipo_T, float minT, float maxT, int iters, int64_t B_global, float lr, float* R, float* T,
                    float* x_rot, float* qs, int64_t B, int J, cudaStream_t st) {
   if (B == 0) return 0;
+  const int nk = keylist.n;
   const size_t smem = (size_t)(2 * iters + nk * 5 * kIpoThreads) * sizeof(float);
   if (smem > 200 * 1024) return ZEDO_E_SHAPE;
-  if (smem > 48 * 1024)
-    ZEDO_CUDA_TRY(cudaFuncSetAttribute(ipo_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024) ZEDO_CUDA_TRY(ensure_max_smem((const void*)ipo_fit_kernel, (int)smem));
   const float lam = (float)(1.0 / ((double)B_global * nk * 2));
   ipo_fit_kernel<<<(unsigned)((B + kIpoThreads - 1) / kIpoThreads), kIpoThreads, smem, st>>>(
-      x0, uv, K, keylist_dev, nk, axes_mask, pelvis_a, pelvis_b, ray_init, ipo_T, minT, maxT, iters, lam, lr, R, T,
+      x0, uv, K, keylist, axes_mask, pelvis_a, pelvis_b, ray_init, ipo_T, minT, maxT, iters, lam, lr, R, T,
       x_rot, qs, B, J);
   ZEDO_LAUNCH_CHECK();
   return 0;

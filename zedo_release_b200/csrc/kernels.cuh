@@ -22,6 +22,12 @@ struct LayerArgs {
   int a_fmt;  // block format of A (common.cuh): 0 = [hi16 | lo16], 1 = [hi16 | hi8 | lo8 | lo16]
   int o_fmt;  // block format of out / resid / addend
 };
+// a short host-side index list (IPO key joints, evaluated joint subset) travels by value in the kernel parameters:
+// no device allocation or copy per call (n = 0: "no list")
+struct IntList {
+  int n = 0;
+  int v[32] = {};
+};
 constexpr int EPI_GN_SILU = 0, EPI_LINEAR_ACT = 1, EPI_LINEAR_F32 = 2;
 int launch_layer_tc(const LayerArgs& a, int bn, int nprod, int epi, int num_sms, cudaStream_t st);
 int launch_layer_tc2(const LayerArgs& a, int nprod, int epi, int num_sms, cudaStream_t st);
@@ -40,7 +46,7 @@ int launch_silu_inplace(float* v, int64_t n, cudaStream_t st);
 int launch_gn_silu_rows(const float* in, const float* cbias, const float* addend, const float* gamma,
                         const float* beta, const float* resid, float* out, int64_t M, int C, float eps,
                         cudaStream_t st);
-int launch_ipo_fit(const float* x0, const float* uv, const float* K, const int* keylist_dev, int nk, int axes_mask,
+int launch_ipo_fit(const float* x0, const float* uv, const float* K, const IntList& keylist, int axes_mask,
                    int pelvis_a, int pelvis_b, int ray_init, float ipo_T, float minT, float maxT, int iters, int64_t B_global, float lr, float* R, float* T,
                    float* x_rot, float* qs, int64_t B, int J, cudaStream_t st);
 int launch_rotopt_forward(const float* q, const float* scale, const float* xk, const float* T0, const float* K,
@@ -50,9 +56,9 @@ int launch_rotopt_backward(const float* q, const float* scale, const float* xk, 
                            cudaStream_t st);
 int launch_hypothesis_std(const float* pred, int64_t N, int S, int J, double* out, cudaStream_t st);
 int launch_pck_counts(const float* pred, const double* gt, const int* select, int64_t N, int S, int J,
-                      const int* subset_dev, int n_sub, unsigned long long* counts, cudaStream_t st);
+                      const IntList& subset, unsigned long long* counts, cudaStream_t st);
 int launch_eval_multi(const float* pred, const double* gt, int protocol2, int64_t N, int S, int J,
-                      const int* subset_dev, int n_sub, double* err_min, int* argmin, double* err_all,
+                      const IntList& subset, double* err_min, int* argmin, double* err_all,
                       double* aligned, cudaStream_t st);
 
 

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) layer_tc_kernel(const Layer
         const __half* w_src = args.W + ((int64_t)nt * num_kb) * 2 * (BN * kBlockK);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          if ((args.dbg & 1) && (tile != (int)blockIdx.x || kb >= S)) {
+          if (ZEDO_EXPERIMENTS && (args.dbg & 1) && (tile != (int)blockIdx.x || kb >= S)) {
             mbar_arrive(&full[stage]);  // experiment: MMA on stale tiles, no L2->SMEM traffic
           } else {
             mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) layer_tc_kernel(const Layer
           const uint64_t b_hi = make_kmajor_desc(b_addr, BN);
           // one MMA consumes K = 16 halves = two 16-byte chunks; chunks are tile_rows*16 bytes apart
           constexpr uint32_t kAStep = (2 * kActTileRows * 16) >> 4, kBStep = (2 * BN * 16) >> 4;
-          if (args.dbg & 2) {  // experiment: feed only, no tensor work
+          if (ZEDO_EXPERIMENTS && (args.dbg & 2)) {  // experiment: feed only, no tensor work
             umma_commit(&empty[stage]);
             if (++stage == S) {
               stage = 0;
@@ -210,8 +210,7 @@ template <int BN, int NPROD, int EPI, int EW>
 static int launch_ew(const LayerArgs& a, int num_sms, cudaStream_t st) {
   using Cfg = TileCfg<BN, NPROD>;
   auto kern = layer_tc_kernel<BN, NPROD, EPI, EW>;
-  // per call, not cached: the attribute is per device and a process may own plans on several devices
-  ZEDO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  ZEDO_CUDA_TRY(ensure_max_smem((const void*)kern, Cfg::kSmemBytes));
   const int tiles = a.m_tiles * a.n_tiles;
   if (tiles == 0) return 0;
   const int grid = tiles < num_sms ? tiles : num_sms;
@@ -222,11 +221,6 @@ static int launch_ew(const LayerArgs& a, int num_sms, cudaStream_t st) {
 
 template <int BN, int NPROD, int EPI>
 static int launch_one(const LayerArgs& a, int num_sms, cudaStream_t st) {
-  if constexpr (BN >= 256) {
-    static const int first16 = getenv("ZEDO_EW_FIRST") ? atoi(getenv("ZEDO_EW_FIRST")) == 16 : 0;
-    if (epi_warps_from_env(BN) == 16 || (first16 && a.num_kb == 1))
-      return launch_ew<BN, NPROD, EPI, 16>(a, num_sms, st);
-  }
   return launch_ew<BN, NPROD, EPI, 8>(a, num_sms, st);
 }
 
@@ -242,9 +236,8 @@ static int launch_nprod(const LayerArgs& a, int nprod, int num_sms, cudaStream_t
 
 // bn: 256 (hidden layers) or 64 (post_dense); nprod: 3 / 2 / 1 MMA passes, 4 = fp8lo (64-channel tiles only); epi: EPI_*
 int launch_layer_tc(const LayerArgs& a_in, int bn, int nprod, int epi, int num_sms, cudaStream_t st) {
-  static const int dbg = getenv("ZEDO_DBG") ? atoi(getenv("ZEDO_DBG")) : 0;
   LayerArgs a = a_in;
-  a.dbg = dbg;
+  a.dbg = ZEDO_EXPERIMENTS ? option_get(ZEDO_OPT_EXPERIMENT) : 0;
   if (nprod == 4) {  // small-batch form of the fp8lo layers: format-1 A blocks, [hi16 | hi8 | lo8] weight tiles
     if (bn != 64 || a.a_fmt != 1) return ZEDO_E_INVALID;
     if (epi == EPI_GN_SILU) return launch_ew<64, 4, EPI_GN_SILU, 8>(a, num_sms, st);

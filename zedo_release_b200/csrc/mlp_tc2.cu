@@ -140,7 +140,7 @@ layer_tc2_kernel(const LayerArgs args) {
         const __half* w_src = args.W + ((int64_t)(2 * nt + (int)rank) * num_kb) * 2 * (Cfg::kHalfN * kBlockK);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          if ((args.dbg & 1) && (pt != pair0 || kb >= S)) {
+          if (ZEDO_EXPERIMENTS && (args.dbg & 1) && (pt != pair0 || kb >= S)) {
             mbar_arrive(&full[stage]);  // experiment: MMA on stale tiles, no L2 -> SMEM traffic
             if (++stage == S) {
               stage = 0;
@@ -265,7 +265,7 @@ template <int NPROD, int EPI, int EW>
 static int launch_pair_ew(const LayerArgs& a, int num_sms, cudaStream_t st) {
   using Cfg = PairCfg<NPROD>;
   auto kern = layer_tc2_kernel<NPROD, EPI, EW>;
-  ZEDO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  ZEDO_CUDA_TRY(ensure_max_smem((const void*)kern, Cfg::kSmemBytes));
   if (a.m_tiles % 2 != 0) return ZEDO_E_SHAPE;
   const int pairs = (a.m_tiles / 2) * a.n_tiles;
   if (pairs == 0) return 0;
@@ -278,8 +278,7 @@ static int launch_pair_ew(const LayerArgs& a, int num_sms, cudaStream_t st) {
 
 template <int NPROD, int EPI>
 static int launch_pair(const LayerArgs& a, int num_sms, cudaStream_t st) {
-  return epi_warps_from_env(256) == 16 ? launch_pair_ew<NPROD, EPI, 16>(a, num_sms, st)
-                                       : launch_pair_ew<NPROD, EPI, 8>(a, num_sms, st);
+  return launch_pair_ew<NPROD, EPI, 8>(a, num_sms, st);
 }
 
 template <int EPI>
@@ -295,9 +294,8 @@ static int launch_pair_nprod(const LayerArgs& a, int nprod, int num_sms, cudaStr
 
 // hidden layers (N multiple of 256, weights packed with 128-row tiles); a.m_tiles must be even
 int launch_layer_tc2(const LayerArgs& a_in, int nprod, int epi, int num_sms, cudaStream_t st) {
-  static const int dbg = getenv("ZEDO_DBG") ? atoi(getenv("ZEDO_DBG")) : 0;
   LayerArgs a = a_in;
-  a.dbg = dbg;
+  a.dbg = ZEDO_EXPERIMENTS ? option_get(ZEDO_OPT_EXPERIMENT) : 0;
   if (epi == EPI_GN_SILU) return launch_pair_nprod<EPI_GN_SILU>(a, nprod, num_sms, st);
   if (epi == EPI_LINEAR_ACT) return launch_pair_nprod<EPI_LINEAR_ACT>(a, nprod, num_sms, st);
   return ZEDO_E_INVALID;

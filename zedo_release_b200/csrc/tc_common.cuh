@@ -197,12 +197,9 @@ __device__ __forceinline__ float silu_fast(float y) {
   return y * r;
 }
 
-// EW epilogue warps per CTA (8 or 16): EW/4 warps share a TMEM lane quarter and split the tile's columns
+// EW epilogue warps per CTA (8; 16 measured slower in r01 -- 96-register cap): EW/4 warps share a TMEM lane quarter
+// and split the tile's columns
 constexpr int tc_threads(int ew) { return 64 + ew * 32; }  // producer warp + MMA warp + epilogue warps
-inline int epi_warps_from_env(int bn) {
-  static const int v = getenv("ZEDO_EW") ? atoi(getenv("ZEDO_EW")) : 8;  // 16 measured slower (96-register cap, r01)
-  return (bn >= 256 && v == 16) ? 16 : 8;
-}
 
 // Fused epilogue of one 128 x BN tile for one thread (= one row x half of the columns):
 // accumulator * descale + per-column constant (+ addend) -> GroupNorm(32) -> SiLU (+ residual) -> hi/lo split

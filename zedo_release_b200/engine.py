@@ -78,6 +78,11 @@ class ScorePlan:
         self._h = nat.plan_create(desc, clean, max_batch, self.device)
         self.capacity = int(nat.lib.zedo_plan_capacity(self._h))
 
+    @_device_scoped
+    def reserve(self, max_steps: int, mode="split3") -> None:
+        """Size the per-step bias tables (and the FP32-mode workspaces) now, so no later call allocates."""
+        nat.check(nat.lib.zedo_plan_reserve(self._h, int(max_steps), _mode(mode), _stream()), "zedo_plan_reserve")
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             nat.lib.zedo_plan_destroy(self._h)
@@ -146,7 +151,8 @@ class ScorePlan:
         steps = int(ts.shape[0])
         if phase_switch is None:
             phase_switch = steps // 5
-        dump_steps = sorted(int(s) for s in dump_steps)
+        requested = [int(s) for s in dump_steps]
+        dump_steps = sorted(set(requested))  # the C ABI takes strictly ascending steps; duplicates are served below
         dump = None
         if dump_steps:
             dump = torch.empty((len(dump_steps),) + tuple(x.shape), dtype=torch.float32, device=x.device)
@@ -155,6 +161,8 @@ class ScorePlan:
                                         float(beta_min), float(beta_max), int(n_scales), _ptr(dump),
                                         nat.i32_array(dump_steps) if dump_steps else None, len(dump_steps),
                                         x.shape[0], _mode(mode), _stream()), "zedo_oil_loop")
+        if dump is not None and sorted(requested) != dump_steps:  # duplicates: one slot per request, sorted order
+            dump = dump[[dump_steps.index(s) for s in sorted(requested)]]
         return dump
 
 
