@@ -73,7 +73,9 @@ def load(root: str | None = None):
         return _CACHE[root]
     if SHIMS not in sys.path:
         sys.path.append(SHIMS)  # behind site-packages: a real ml_collections / prettytable wins
-    with _isolated_lib_namespace():
+    import warnings
+    with _isolated_lib_namespace(), warnings.catch_warnings():
+        warnings.simplefilter("ignore", SyntaxWarning)  # a docstring of the reference's transforms.py holds "\m"
         sys.path.insert(0, root)
         try:
             import torch

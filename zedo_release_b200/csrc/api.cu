@@ -8,7 +8,6 @@
 #include <map>
 #include <mutex>
 #include <new>
-#include <set>
 #include <string>
 #include <vector>
 
@@ -44,7 +43,7 @@ Options& options() {
   return o;
 }
 std::mutex g_smem_mu;
-std::set<std::pair<int, const void*>> g_smem_set;
+std::map<std::pair<int, const void*>, int> g_smem_set;  // (device, kernel) -> largest size granted
 }  // namespace
 
 int option_get(int opt) { return options().v[opt].load(std::memory_order_relaxed); }
@@ -55,9 +54,10 @@ cudaError_t ensure_max_smem(const void* func, int bytes) {
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   std::lock_guard<std::mutex> lock(g_smem_mu);
-  if (g_smem_set.count({dev, func})) return cudaSuccess;
+  auto it = g_smem_set.find({dev, func});
+  if (it != g_smem_set.end() && it->second >= bytes) return cudaSuccess;
   e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e == cudaSuccess) g_smem_set.insert({dev, func});
+  if (e == cudaSuccess) g_smem_set[{dev, func}] = bytes;
   return e;
 }
 

@@ -320,20 +320,27 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
 def run_pose_optimisation(plan: ScorePlan, db_2d: torch.Tensor, K: torch.Tensor, clusters: torch.Tensor, cfg: dict,
                           hypo: int = 1, mode="split3", t_start: float = 0.1, b_global: Optional[int] = None,
                           steps: Optional[int] = None, phase_switch: Optional[int] = None,
-                          pelvis: Tuple[int, int] = (0, 0), ray_init: bool = False, use_conf: bool = True
-                          ) -> torch.Tensor:
+                          pelvis: Tuple[int, int] = (0, 0), ray_init: bool = False, use_conf: bool = True,
+                          root_relative: bool = True, per_hypothesis_cluster: bool = True) -> torch.Tensor:
     """db_2d [B,J,3] = (u,v,conf), K [B,3,3], clusters [S,J,3] (cluster file content).
     Returns batch_results [B, hypo, J, 3] (the array run/opt_main.py:224 hands to eval_multi).
     ``b_global``: batch size of the IPO loss mean when the poses are a shard of a larger batch.
-    Infant driver (run/opt_main_infant.py): ``phase_switch=950``, ``ray_init=True``, ``use_conf=False``,
-    ``pelvis=(0, 3)`` for SyRIP.
+    Infant driver (run/opt_main_infant.py:236-334): ``phase_switch=950``, ``ray_init=True``, ``use_conf=False``,
+    ``pelvis=(0, 3)`` for SyRIP, and -- because that driver multiplies the template in without subtracting its root
+    and uses the same template for every hypothesis (:249-251) -- ``root_relative=False``,
+    ``per_hypothesis_cluster=False`` (hypothesis ``sid`` then starts from ``clusters[0]``, so ``hypo`` may exceed
+    ``len(clusters)``).
     """
     db_2d, K, clusters = _f32(db_2d, "db_2d"), _f32(K, "K"), _f32(clusters, "clusters")
     B, J = db_2d.shape[0], db_2d.shape[1]
     uv = db_2d[:, :, :2].contiguous()
     n_steps = int(cfg["OIL_iterations"] if steps is None else steps)
     ts = linspace_schedule(t_start, float(cfg["sampling_eps"]), n_steps)
-    rel = (clusters - clusters[:, 0:1, :]).contiguous()
+    rel = (clusters - clusters[:, 0:1, :]).contiguous() if root_relative else clusters.contiguous()
+    if not per_hypothesis_cluster:
+        rel = rel[0:1].expand(hypo, J, 3).contiguous()
+    elif hypo > rel.shape[0]:
+        raise ValueError(f"hypo={hypo} exceeds the {rel.shape[0]} cluster poses supplied (run/opt_main.py:167-168)")
     out = torch.empty((B, hypo, J, 3), dtype=torch.float32, device=db_2d.device)
     # Hypotheses are independent runs of the same loop (opt_main.py:166): as many as fit the plan are stacked
     # along the batch axis (row = h * B + pose) so one IPO kernel and one OIL loop serve the whole group.

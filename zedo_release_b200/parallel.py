@@ -66,24 +66,42 @@ def global_batch_mean(per_pose: torch.Tensor) -> torch.Tensor:
     return (acc[0] / acc[1]).to(per_pose.dtype)
 
 
-def run_sharded(plan_factory, db_2d, K, clusters, cfg, hypo=1, mode="split3", gt=None, protocol2=False,
-                actions=None):
-    """The whole job on this rank's shard: slice the (host) arrays by ``shard_range``, run IPO + OIL
-    (IPO gradients scaled by the GLOBAL batch: the reference's loss is a mean over the whole batch,
-    run/opt_main.py:191), optionally evaluate, gather.  Returns (results [N,S,J,3] on every rank,
-    (err_min [N], argmin [N]) or None)."""
+def run_sharded(plan_or_factory, db_2d, K, clusters, cfg, hypo=1, mode="split3", gt=None, protocol2=False,
+                actions=None, local_shard=False, n_total=None, gather_results=True, **run_kw):
+    """The whole job on this rank's shard: slice the (host) arrays by ``shard_range``, copy the shard to the device,
+    run IPO + OIL (IPO gradients scaled by the GLOBAL batch: the reference's loss is a mean over the whole batch,
+    run/opt_main.py:191), optionally evaluate, and gather with ONE ``all_gather_into_tensor`` per result tensor
+    (results [N,S,J,3] f32, err_min [N] f64, argmin [N] i32).  Returns
+    (results [N,S,J,3] on every rank -- the local shard when ``gather_results`` is false --,
+    (err_min [N], argmin [N]) or None).
+
+    ``plan_or_factory``: a ``ScorePlan`` that is large enough, or a callable ``n_local -> ScorePlan``.
+    ``local_shard=True``: the arrays passed ARE this rank's shard (weak scaling: every rank generates its own
+    poses) and ``n_total`` is the global number of poses.  ``run_kw`` goes to ``run_pose_optimisation`` (infant
+    driver switches)."""
     from . import engine
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
-    n = db_2d.shape[0]
-    lo, hi = shard_range(n, rank, world)
+    if local_shard:
+        n = int(n_total if n_total is not None else db_2d.shape[0] * world)
+        lo, hi = shard_range(n, rank, world)
+        assert hi - lo == db_2d.shape[0], "local shard does not follow shard_range()"
+        sl = slice(None)
+    else:
+        n = db_2d.shape[0]
+        lo, hi = shard_range(n, rank, world)
+        sl = slice(lo, hi)
     dev = torch.device("cuda", torch.cuda.current_device())
-    plan = plan_factory(hi - lo)
-    res = engine.run_pose_optimisation(plan, torch.as_tensor(db_2d[lo:hi], device=dev),
-                                       torch.as_tensor(K[lo:hi], device=dev), torch.as_tensor(clusters, device=dev),
-                                       cfg, hypo=hypo, mode=mode, b_global=n)
+    plan = plan_or_factory(hi - lo) if callable(plan_or_factory) else plan_or_factory
+
+    def to_dev(a, dtype=torch.float32):
+        t = a if isinstance(a, torch.Tensor) else torch.as_tensor(a)
+        return t.to(device=dev, dtype=dtype, non_blocking=True)
+
+    res = engine.run_pose_optimisation(plan, to_dev(db_2d[sl]), to_dev(K[sl]), to_dev(clusters), cfg, hypo=hypo,
+                                       mode=mode, b_global=n, **run_kw)
     ev = None
     if gt is not None:
-        err, idx = engine.eval_multi(res, torch.as_tensor(gt[lo:hi], device=dev), protocol2=protocol2)
+        err, idx = engine.eval_multi(res, to_dev(gt[sl], torch.float64), protocol2=protocol2)
         ev = (gather_rows(err, n), gather_rows(idx, n))
-    return gather_rows(res, n), ev
+    return (gather_rows(res, n) if gather_results else res), ev
