@@ -431,7 +431,7 @@ def main():
     ap.add_argument("--poses-total", type=int, default=None, help="override: poses of the whole job (strong scaling)")
     ap.add_argument("--hypo", type=int, default=None)
     ap.add_argument("--oil-steps", type=int, default=1000, help="OIL steps per pose (reference: 1000)")
-    ap.add_argument("--mode", default="split3", choices=["split3", "fp8lo", "split2", "fp16", "fp32"])
+    ap.add_argument("--mode", default="fp8lo", choices=["split3", "fp8lo", "split2", "fp16", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--dataset", default=None, choices=["h36m", "pw3d", "mini", "syrip"],
                     help="ZeDO config block (IPO key joints / axes / scale clamp; infant configs switch phase at 95%%)")

@@ -40,12 +40,13 @@ extern "C" {
 #define ZEDO_E_STATE     (-5)  /* call order violated (e.g. step before set_schedule) */
 
 /* GEMM arithmetic of the score network (all accumulate in float32) */
-#define ZEDO_GEMM_SPLIT3 0  /* tcgen05, fp16 hi/lo 3-product split: parity mode (default) */
+#define ZEDO_GEMM_SPLIT3 0  /* tcgen05, fp16 hi/lo 3-product split (2^-22 product error)        */
 #define ZEDO_GEMM_FP16   1  /* tcgen05, single-pass fp16 inputs: fast mode             */
 #define ZEDO_GEMM_FP32   2  /* CUDA-core float32 FFMA: validation kernel                */
 #define ZEDO_GEMM_SPLIT2 3  /* tcgen05, fp16 activations x (hi+lo) weights: 2 MMA passes  */
 #define ZEDO_GEMM_FP8LO  4  /* tcgen05, fp16 main product + the two low-order products in e4m3 (kind::f8f6f4):
-                               2 fp16-pass equivalents, 2^-15 product error (split3: 2^-22, split2: 2^-12).
+                               2 fp16-pass equivalents, 2^-15 product error (split3: 2^-22, split2: 2^-12); holds every parity
+                               bound of split3 and is what the host layer uses when no mode is named.
                                A plan with a 1024x1024 weight whose max/rms exceeds 16 (too heavy-tailed for one
                                e4m3 scale per matrix) runs this mode as SPLIT3; ZEDO_FP8LO_FORCE=1 overrides. */
 
@@ -125,6 +126,31 @@ int zedo_grad_field(const float* uv, const float* x, const float* K, float* conf
 int zedo_sde_step(zedo_plan* plan, const float* x, float t, const float* z, int32_t predictor,
                   int32_t probability_flow, float beta_min, float beta_max, int32_t n_scales,
                   float* x_next, float* x_mean, int64_t B, int32_t gemm_mode, void* stream);
+
+/* ---- noise-bearing predictors / correctors with caller-injected noise ---------------------------------
+ * Replaces: AncestralSamplingPredictor (sampling.py:208-244), LangevinCorrector (:258-287) and
+ * AnnealedLangevinDynamics (:290-324) over get_score_fn (utils.py:751-795), for a batch-uniform time.
+ * Two calls per update so that a sharded run can make the Langevin batch means GLOBAL in between:
+ *
+ *   zedo_score_stats   network forward with time label `label` (999 t for VP / sub-VP, the marginal std for a
+ *                      continuous VE SDE); the output stays in the plan.  When `stats` != NULL it receives
+ *                      { sum over rows of |score_row|_2, sum over rows of |z_row|_2, rows } (device double[3],
+ *                      overwritten, summed in a fixed order): sampling.py:281-282 before the `.mean()`.
+ *                      A multi-GPU caller all-reduces (SUM) `stats` over the ranks here.
+ *   zedo_noise_update  the elementwise update from the network output of the preceding zedo_score_stats /
+ *                      zedo_score_forward call on this plan (ZEDO_E_STATE if B differs), one float32 rounding per
+ *                      tensor op of the reference.  x, z [B,J,3]; x_next / x_mean may be NULL or alias x.
+ *
+ * std_div: score = (-net) / std_div (VP, sub-VP: the marginal std) or score = net when std_div == 0 (VE). */
+#define ZEDO_UPD_ANCESTRAL_VP 0  /* p0 = discrete_betas[timestep]                                  (:233-241) */
+#define ZEDO_UPD_ANCESTRAL_VE 1  /* p0 = sigma, p1 = adjacent sigma                                (:220-231) */
+#define ZEDO_UPD_LANGEVIN     2  /* p0 = snr, p1 = alpha; step from the batch means in `stats`      (:277-285) */
+#define ZEDO_UPD_ALD          3  /* p0 = snr, p1 = alpha, p2 = marginal std; stats unused           (:314-321) */
+int zedo_score_stats(zedo_plan* plan, const float* x, float label, const float* z, float std_div, double* stats,
+                     int64_t B, int32_t gemm_mode, void* stream);
+int zedo_noise_update(zedo_plan* plan, int32_t kind, const float* x, const float* z, float std_div, float p0,
+                      float p1, float p2, const double* stats, float* x_next, float* x_mean, int64_t B,
+                      void* stream);
 
 /* ---- the whole OIL loop ---------------------------------------------------------------------
  * Replaces: the `for i in range(sample_num)` body of run/opt_main.py:202-220 (and

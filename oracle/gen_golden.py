@@ -333,6 +333,47 @@ def main():
     ck.check("ReverseDiffusion (noise) x_mean", xmo2, xmr2.numpy(), 2e-6)
     out["noise"] = dict(z=z, em_x=xr.numpy(), em_mean=xmr.numpy(), rd_x=xr2.numpy(), rd_mean=xmr2.numpy())
 
+    # ---- 5b. the remaining registered updates with injected noise (sampling.py:208-324): VP / VE SDEs ------------
+    print("ancestral / Langevin / ALD with injected noise (VPSDE, VESDE)")
+    vp = R.sde_lib.VPSDE(beta_min=0.1, beta_max=20.0, N=1000, T=0.1)
+    ve = R.sde_lib.VESDE(sigma_min=0.01, sigma_max=50.0, N=1000, T=0.1)
+    sf_vp = R.mutils.get_score_fn(vp, model, train=False, continuous=True)
+    sf_ve = R.mutils.get_score_fn(ve, model, train=False, continuous=True)
+    zs = [np.random.default_rng(20 + k).normal(0, 1, xb.shape).astype(np.float32) for k in range(2)]
+
+    def with_noise(fn):
+        it = iter(zs)
+        _o = torch.randn_like
+        torch.randn_like = lambda x, *a, **k: torch.tensor(next(it))
+        try:
+            with torch.no_grad():
+                return tuple(v.numpy() for v in fn())
+        finally:
+            torch.randn_like = _o
+
+    vt = torch.ones(8) * t_i
+    nz = {}
+    nz["anc_vp_x"], nz["anc_vp_mean"] = with_noise(lambda: R.sampling.AncestralSamplingPredictor(vp, sf_vp).update_fn(
+        torch.tensor(xb), vt, None, None))
+    nz["anc_ve_x"], nz["anc_ve_mean"] = with_noise(lambda: R.sampling.AncestralSamplingPredictor(ve, sf_ve).update_fn(
+        torch.tensor(xb), vt, None, None))
+    nz["lang_x"], nz["lang_mean"] = with_noise(lambda: R.sampling.LangevinCorrector(vp, sf_vp, 0.16, 2).update_fn(
+        torch.tensor(xb), vt, None, None))
+    nz["ald_x"], nz["ald_mean"] = with_noise(lambda: R.sampling.AnnealedLangevinDynamics(vp, sf_vp, 0.16, 1).update_fn(
+        torch.tensor(xb), vt, None, None))
+    tf = np.float32(t_i)
+    for tag, got in (("anc_vp", zo.ancestral_update_vp(W, xb, tf, zs[0])), ("anc_ve", zo.ancestral_update_ve(W, xb, tf, zs[0])),
+                     ("lang", zo.langevin_update_vp(W, xb, tf, zs, snr=0.16, n_steps=2)),
+                     ("ald", zo.langevin_update_vp(W, xb, tf, zs, snr=0.16, n_steps=1, ald=True))):
+        ck.check(f"{tag} (injected noise) x", got[0], nz[f"{tag}_x"], 5e-6)
+        ck.check(f"{tag} (injected noise) x_mean", got[1], nz[f"{tag}_mean"], 5e-6)
+    try:
+        R.sampling.LangevinCorrector(sde, score_fn, 0.16, 1).update_fn(torch.tensor(xb), vt, None, None)
+        raise SystemExit("expected the reference's Langevin corrector to fail on the sub-VP SDE (no `alphas`)")
+    except AttributeError:
+        pass
+    out["noise_vp"] = dict(x=xb, t=np.float32(t_i), z0=zs[0], z1=zs[1], **nz)
+
     # ---- 6. IPO: RotOpt + Adam ----------------------------------------------------------------------
     print("IPO (RotOpt + Adam)")
     ipo = {}

@@ -74,6 +74,10 @@ def load(root: str | None = None):
     if SHIMS not in sys.path:
         sys.path.append(SHIMS)  # behind site-packages: a real ml_collections / prettytable wins
     import warnings
+    try:  # the reference's model.py imports torchvision.utils; importing it first keeps torchvision's own import-time
+        import torchvision.utils  # noqa: F401  source inspection away from the reference's namespace package `lib`
+    except Exception:
+        pass
     with _isolated_lib_namespace(), warnings.catch_warnings():
         warnings.simplefilter("ignore", SyntaxWarning)  # a docstring of the reference's transforms.py holds "\m"
         sys.path.insert(0, root)

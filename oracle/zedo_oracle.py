@@ -314,6 +314,75 @@ def langevin_update(W: Weights, x, t, noises: Sequence[np.ndarray], snr=0.16, n_
     return x, x_mean
 
 
+def score_fn_vp(W: Weights, x, t, forward=score_forward):
+    """``get_score_fn`` VP branch, continuous (utils.py:751-777): -model(x, 999 t) / sqrt(1 - exp(2 lmc))."""
+    t = f32(t)
+    return (-forward(W, x, t * f32(999)) / vp_marginal_std(t)).astype(f32)
+
+
+def ve_sigma(t, sigma_min=0.01, sigma_max=50.0):
+    """``VESDE.marginal_prob`` std (sde_lib.py:241-244): sigma_min (sigma_max / sigma_min)^t."""
+    return (f32(sigma_min) * np.power(f32(sigma_max / sigma_min), f32(t), dtype=f32)).astype(f32)
+
+
+def score_fn_ve(W: Weights, x, t, forward=score_forward):
+    """``get_score_fn`` VE branch, continuous (utils.py:779-795): model(x, labels = sigma(t)), no rescale."""
+    return forward(W, x, ve_sigma(t)).astype(f32)
+
+
+def _timestep(t, n_scales=NUM_SCALES, T=T_START):
+    """``(t * (sde.N - 1) / sde.T).long()`` in float32 (sampling.py:234,273)."""
+    return int(np.trunc(f32(f32(t) * f32(n_scales - 1)) / f32(T)))
+
+
+def vp_discrete_betas(beta_min=BETA_MIN, beta_max=BETA_MAX, n_scales=NUM_SCALES):
+    """``VPSDE.discrete_betas`` (sde_lib.py:125): torch.linspace(beta_min / N, beta_max / N, N), float32."""
+    return oil_time_grid(n_scales, beta_min / n_scales, beta_max / n_scales)
+
+
+def ancestral_update_vp(W: Weights, x, t, z, forward=score_forward, T=T_START):
+    """``AncestralSamplingPredictor.vpsde_update_fn`` (sampling.py:233-241)."""
+    beta = vp_discrete_betas()[_timestep(t, T=T)]
+    score = score_fn_vp(W, x, t, forward)
+    x_mean = ((x + beta * score) / np.sqrt(f32(1.0) - beta, dtype=f32)).astype(f32)
+    return (x_mean + np.sqrt(beta, dtype=f32) * z).astype(f32), x_mean
+
+
+def ancestral_update_ve(W: Weights, x, t, z, forward=score_forward, T=T_START, sigma_min=0.01, sigma_max=50.0):
+    """``AncestralSamplingPredictor.vesde_update_fn`` (sampling.py:220-231)."""
+    sig = np.exp(np.linspace(np.log(sigma_min), np.log(sigma_max), NUM_SCALES).astype(f32), dtype=f32)
+    ts = _timestep(t, T=T)
+    sigma, adj = sig[ts], (f32(0.0) if ts == 0 else sig[ts - 1])
+    score = score_fn_ve(W, x, t, forward)
+    x_mean = (x + score * (sigma ** 2 - adj ** 2)).astype(f32)
+    std = np.sqrt((adj ** 2 * (sigma ** 2 - adj ** 2)) / (sigma ** 2), dtype=f32)
+    return (x_mean + std * z).astype(f32), x_mean
+
+
+def langevin_update_vp(W: Weights, x, t, noises: Sequence[np.ndarray], snr=0.16, n_steps=1, forward=score_forward,
+                       T=T_START, norm_means: Optional[Tuple[float, float]] = None, ald=False):
+    """``LangevinCorrector.update_fn`` (sampling.py:258-287) / ``AnnealedLangevinDynamics.update_fn`` (:290-324,
+    ``ald=True``) for the VP SDE (the only SDE of the three that defines ``alphas``, sde_lib.py:126)."""
+    alpha = f32(1.0) - vp_discrete_betas()[_timestep(t, T=T)]
+    std_m = vp_marginal_std(t)
+    x_mean = x
+    for i in range(n_steps):
+        grad = score_fn_vp(W, x, t, forward)
+        noise = noises[i].astype(f32)
+        if ald:
+            step = (f32(snr) * std_m) ** 2 * f32(2) * alpha
+        else:
+            if norm_means is None:
+                gn = np.linalg.norm(grad.reshape(grad.shape[0], -1), axis=-1).astype(f32).mean(dtype=f32)
+                nn_ = np.linalg.norm(noise.reshape(noise.shape[0], -1), axis=-1).astype(f32).mean(dtype=f32)
+            else:
+                gn, nn_ = f32(norm_means[0]), f32(norm_means[1])
+            step = (f32(snr) * nn_ / gn) ** 2 * f32(2) * alpha
+        x_mean = (x + step * grad).astype(f32)
+        x = (x_mean + np.sqrt(step * f32(2), dtype=f32) * noise).astype(f32)
+    return x, x_mean
+
+
 def pc_sampler_step(W: Weights, denoise_x, t, denoise=True, probability_flow=True, z=None,
                     forward=score_forward):
     """One call of ``pc_sampler`` (sampling.py:450-527) for the shipped configuration

@@ -95,3 +95,57 @@ def test_plan_on_a_non_current_device():
     p0.close()
     p1.close()
     assert torch.cuda.current_device() == 0
+
+
+def _langevin_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch
+    import torch.distributed as dist
+    import zedo_release_b200 as zr
+    from zedo_release_b200 import parallel
+    r, w, local = parallel.init_from_env("nccl")
+    dev = torch.device("cuda", local)
+    N = 1001
+    rng = np.random.default_rng(9)
+    x = rng.normal(0, 0.4, (N, 17, 3)).astype(np.float32)
+    z = rng.normal(0, 1.0, (N, 17, 3)).astype(np.float32)
+    lo, hi = zr.shard_range(N, r, w)
+    plan = zr.ScorePlan(zo.make_weights(seed=0), n_joints=17, max_batch=hi - lo, device=local)
+    xs, zs = torch.tensor(x[lo:hi], device=dev), torch.tensor(z[lo:hi], device=dev)
+    stats = plan.score_stats(xs, 43.7, z=zs, std_div=0.31, want_stats=True)
+    parallel.global_sum_(stats)  # NCCL all_reduce of (sum |score_row|, sum |z_row|, rows)
+    xn, xm = plan.noise_update("langevin", xs, zs, 0.31, 0.16, 0.998, stats=stats)
+    full = parallel.gather_rows(xn, N)
+    if r == 0:
+        np.savez(os.path.join(out_dir, "langevin.npz"), x=full.cpu().numpy(), stats=stats.cpu().numpy())
+    plan.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_langevin_step_size_uses_the_global_batch_mean(tmp_path):
+    """sampling.py:281-283: the Langevin step size takes BATCH means of the gradient / noise norms; sharded over two
+    ranks the per-rank sums are all-reduced over NCCL between the two fused calls and the result equals the
+    single-GPU run on the whole batch."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    import zedo_release_b200 as zr
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_langevin_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(tmp_path / "langevin.npz")
+    N = 1001
+    rng = np.random.default_rng(9)
+    x = torch.tensor(rng.normal(0, 0.4, (N, 17, 3)).astype(np.float32), device="cuda:0")
+    z = torch.tensor(rng.normal(0, 1.0, (N, 17, 3)).astype(np.float32), device="cuda:0")
+    plan = zr.ScorePlan(zo.make_weights(seed=0), n_joints=17, max_batch=N, device=0)
+    stats = plan.score_stats(x, 43.7, z=z, std_div=0.31, want_stats=True)
+    xn, _ = plan.noise_update("langevin", x, z, 0.31, 0.16, 0.998, stats=stats)
+    plan.close()
+    assert got["stats"][2] == N and np.allclose(got["stats"], stats.cpu().numpy(), rtol=1e-12)
+    assert np.allclose(got["x"], xn.cpu().numpy(), rtol=0, atol=1e-6)

@@ -170,3 +170,15 @@ def test_c1_golden_matches_the_synthetic_generator(golden):
     gr, _ = zo.gradient_field(ds["db_2d"][:8, :, :2], x_rot[:8], ds["camera_param"][:8], t=g["T"][:8].reshape(8, 1, 3),
                               conf=ds["db_2d"][:8, :, 2].copy())
     assert np.isfinite(gr).all() and np.abs(gr).max() < 5.0
+
+
+def test_noise_bearing_updates_vp_ve(golden):
+    """Ancestral sampling (VP / VE), Langevin corrector (2 steps, batch-mean norms) and annealed Langevin dynamics with
+    injected noise, recorded from the reference's classes (sampling.py:208-324) on VPSDE / VESDE."""
+    W = zo.make_weights(seed=0)
+    g = golden("noise_vp")
+    x, t, zs = g["x"], np.float32(g["t"]), [g["z0"], g["z1"]]
+    for tag, got in (("anc_vp", zo.ancestral_update_vp(W, x, t, zs[0])), ("anc_ve", zo.ancestral_update_ve(W, x, t, zs[0])),
+                     ("lang", zo.langevin_update_vp(W, x, t, zs, snr=0.16, n_steps=2)),
+                     ("ald", zo.langevin_update_vp(W, x, t, zs, snr=0.16, n_steps=1, ald=True))):
+        assert rel_err(got[0], g[f"{tag}_x"]) < 5e-6 and rel_err(got[1], g[f"{tag}_mean"]) < 5e-6, tag

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libzedo_b200.so")
 GEMM_SPLIT3, GEMM_FP16, GEMM_FP32, GEMM_SPLIT2, GEMM_FP8LO = 0, 1, 2, 3, 4
 NET_SCORE_FC_ADV, NET_CONTROL = 0, 1
 PRED_EULER_MARUYAMA, PRED_REVERSE_DIFFUSION = 0, 1
+UPD_ANCESTRAL_VP, UPD_ANCESTRAL_VE, UPD_LANGEVIN, UPD_ALD = 0, 1, 2, 3
 OPT_GEOM_KERNEL, OPT_PDL, OPT_SMALL_TILES, OPT_CTA_PAIRS, OPT_FP8LO_FORCE, OPT_EXPERIMENT = range(6)
 
 #: every symbol ``include/zedo_b200.h`` declares (checked by tests/test_abi.py)
@@ -24,7 +25,8 @@ EXPORTS = (
     "zedo_sde_step", "zedo_oil_loop", "zedo_ipo_fit", "zedo_rotopt_forward", "zedo_rotopt_backward",
     "zedo_eval_multi", "zedo_strerror", "zedo_abi_version", "zedo_launch_count", "zedo_subvp_scalars",
     "zedo_blocked_offset", "zedo_plan_profile", "zedo_plan_profile_read", "zedo_ipo_fit_ex", "zedo_pck_counts",
-    "zedo_hypothesis_std", "zedo_plan_reserve", "zedo_set_option", "zedo_get_option",
+    "zedo_hypothesis_std", "zedo_plan_reserve", "zedo_set_option", "zedo_get_option", "zedo_score_stats",
+    "zedo_noise_update",
 )
 
 
@@ -56,6 +58,8 @@ def _load() -> C.CDLL:
         "zedo_set_option": (C.c_int, [i32, i32]),
         "zedo_get_option": (C.c_int, [i32, C.POINTER(i32)]),
         "zedo_score_forward": (C.c_int, [vp, p, f32, p, i64, i32, vp]),
+        "zedo_score_stats": (C.c_int, [vp, p, f32, p, f32, p, i64, i32, vp]),
+        "zedo_noise_update": (C.c_int, [vp, i32, p, p, f32, f32, f32, f32, p, p, p, i64, vp]),
         "zedo_grad_field": (C.c_int, [p, p, p, p, p, i32, i32, p, p, i64, i32, vp]),
         "zedo_sde_step": (C.c_int, [vp, p, f32, p, i32, i32, f32, f32, i32, p, p, i64, i32, vp]),
         "zedo_oil_loop": (C.c_int, [vp, p, p, p, p, p, C.POINTER(f32), i32, i32, f32, f32, i32, p,

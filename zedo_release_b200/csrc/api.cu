@@ -210,6 +210,8 @@ struct zedo_plan {
   float* eps = nullptr;            // [m_pad, 64]
   std::vector<float*> act32;       // validation mode, lazily allocated [m_pad, H]
   float* x32 = nullptr;            // [m_pad, D] scratch pose buffer
+  float* row_norms = nullptr;      // [m_pad, 2] per-row |score|, |z| of the Langevin corrector
+  int64_t eps_rows = -1;           // rows of the network output currently held in `eps` (-1: none)
   // bias tables
   int table_steps = 0;
   float* t999_dev = nullptr;
@@ -835,6 +837,7 @@ static int plan_create_impl(zedo_plan** out, const zedo_net_desc* desc, int32_t 
   }
   PLAN_TRY(dev_alloc(p, &p->eps, (size_t)p->m_pad * 64));
   PLAN_TRY(dev_alloc(p, &p->x32, (size_t)p->m_pad * D));
+  PLAN_TRY(dev_alloc(p, &p->row_norms, (size_t)p->m_pad * 2));
   PLAN_TRY(ensure_tables(p, 1, (cudaStream_t)0));
   PLAN_TRY((int)cudaDeviceSynchronize());
 #undef NEED
@@ -939,11 +942,40 @@ int zedo_score_forward(zedo_plan* plan, const float* x, float t999, float* out, 
   if (B == 0) return 0;
   if (!x || !out) return ZEDO_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
+  plan->eps_rows = -1;
   if ((rc = build_tables(plan, &t999, 1, st))) return rc;
   if ((rc = net_forward(plan, x, plan->table, B, gemm_mode, false, st))) return rc;
+  plan->eps_rows = B;
   ZEDO_CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)plan->D * sizeof(float), plan->eps, 64 * sizeof(float),
                                   (size_t)plan->D * sizeof(float), (size_t)B, cudaMemcpyDeviceToDevice, st));
   return 0;
+}
+
+int zedo_score_stats(zedo_plan* plan, const float* x, float label, const float* z, float std_div, double* stats,
+                     int64_t B, int32_t gemm_mode, void* stream) {
+  int rc = check_batch(plan, B);
+  if (rc) return rc;
+  if (B == 0) return 0;
+  if (!x || (stats && !z) || std_div < 0.f) return ZEDO_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  plan->eps_rows = -1;
+  if ((rc = build_tables(plan, &label, 1, st))) return rc;
+  if ((rc = net_forward(plan, x, plan->table, B, gemm_mode, false, st))) return rc;
+  plan->eps_rows = B;
+  if (stats) return launch_row_norm_stats(plan->eps, 64, z, std_div, plan->row_norms, stats, B, plan->D, st);
+  return 0;
+}
+
+int zedo_noise_update(zedo_plan* plan, int32_t kind, const float* x, const float* z, float std_div, float p0, float p1,
+                      float p2, const double* stats, float* x_next, float* x_mean, int64_t B, void* stream) {
+  int rc = check_batch(plan, B);
+  if (rc) return rc;
+  if (kind < ZEDO_UPD_ANCESTRAL_VP || kind > ZEDO_UPD_ALD || !x || std_div < 0.f) return ZEDO_E_INVALID;
+  if (kind == ZEDO_UPD_LANGEVIN && !stats) return ZEDO_E_INVALID;
+  if (B == 0) return 0;
+  if (plan->eps_rows != B) return ZEDO_E_STATE;  // needs the network output of a forward over these B rows
+  return launch_noise_update(kind, x, plan->eps, 64, z, std_div, p0, p1, p2, stats, x_next, x_mean, B, plan->D,
+                             (cudaStream_t)stream);
 }
 
 int zedo_grad_field(const float* uv, const float* x, const float* K, float* conf, float* T, int32_t solve_T,
@@ -965,6 +997,7 @@ int zedo_sde_step(zedo_plan* plan, const float* x, float t, const float* z, int3
   if (B == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const float t999 = t * 999.0f;  // labels = t * 999 (utils.py:762)
+  plan->eps_rows = -1;
   if ((rc = build_tables(plan, &t999, 1, st))) return rc;
   if ((rc = net_forward(plan, x, plan->table, B, gemm_mode, false, st))) return rc;
   const SdeCoef c = subvp_coef(t, beta_min, beta_max, n_scales);
@@ -984,6 +1017,7 @@ static int oil_loop_impl(zedo_plan* plan, float* x, float* T, const float* uv, c
       return ZEDO_E_INVALID;  // strictly ascending, inside the schedule
   if (B == 0 || steps == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  plan->eps_rows = -1;
   const int J = plan->desc.n_joints, D = plan->D;
   std::vector<float> t999((size_t)steps);
   for (int i = 0; i < steps; ++i) t999[i] = t_sched[i] * 999.0f;

@@ -554,3 +554,121 @@ int launch_sde_update(const float* x, const float* eps, int ld_eps, const float*
 }
 
 }  // namespace zedo
+
+// ---- noise-bearing predictor / corrector updates with caller-injected noise (sampling.py:208-324) -------------
+namespace zedo {
+
+// score of one element under get_score_fn's conventions (utils.py:751-795): VP / sub-VP: (-eps) / std; VE: eps
+__device__ __forceinline__ float score_of(float e, float std_div) { return std_div > 0.f ? __fdiv_rn(-e, std_div) : e; }
+
+// per row: |score_row|_2 and |z_row|_2 (torch.norm(v.reshape(B, -1), dim=-1), sampling.py:281-282); one warp per row
+__global__ void __launch_bounds__(256)
+row_norms_kernel(const float* __restrict__ eps, int ld_eps, const float* __restrict__ z, float std_div,
+                 float* __restrict__ norms, int64_t B, int D) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  griddep_wait();
+  if (row >= B) return;
+  float sg = 0.f, sz = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float g = score_of(eps[row * ld_eps + c], std_div);
+    const float zz = z[row * D + c];
+    sg = fmaf(g, g, sg);
+    sz = fmaf(zz, zz, sz);
+  }
+  sg = warp_sum(sg);
+  sz = warp_sum(sz);
+  if (lane == 0) {
+    norms[2 * row] = sqrtf(sg);
+    norms[2 * row + 1] = sqrtf(sz);
+  }
+}
+
+// stats = (sum_rows |score_row|, sum_rows |z_row|, rows): one CTA, fixed summation order -> the same bits on every run
+__global__ void __launch_bounds__(1024) norm_stats_kernel(const float* __restrict__ norms, int64_t B, double* stats) {
+  __shared__ double sh[2][1024];
+  double a = 0.0, b = 0.0;
+  for (int64_t r = threadIdx.x; r < B; r += 1024) {
+    a += (double)norms[2 * r];
+    b += (double)norms[2 * r + 1];
+  }
+  sh[0][threadIdx.x] = a;
+  sh[1][threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    stats[0] = sh[0][0];
+    stats[1] = sh[1][0];
+    stats[2] = (double)B;
+  }
+}
+
+// One rounding per tensor op of the reference, t uniform over the batch:
+//   ancestral VP (:233-241)  x_mean = (x + beta score) / sqrt(1 - beta);           x' = x_mean + sqrt(beta) z        p0 = beta
+//   ancestral VE (:220-231)  x_mean = x + score (s^2 - a^2);  x' = x_mean + sqrt(a^2 (s^2 - a^2) / s^2) z   p0 = s, p1 = a
+//   Langevin     (:277-285)  step = (snr |z|_mean / |grad|_mean)^2 * 2 * alpha;  x_mean = x + step grad;
+//                            x' = x_mean + sqrt(step * 2) z                                    p0 = snr, p1 = alpha
+//   ALD          (:314-321)  step = (snr std_m)^2 * 2 * alpha; same update                    p0 = snr, p1 = alpha, p2 = std_m
+__global__ void noise_update_kernel(int kind, const float* __restrict__ x, const float* __restrict__ eps, int ld_eps,
+                                    const float* __restrict__ z, float std_div, float p0, float p1, float p2,
+                                    const double* __restrict__ stats, float* x_next, float* x_mean, int64_t B, int D) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  griddep_wait();
+  if (idx >= B * D) return;
+  const int64_t row = idx / D;
+  const int e = (int)(idx - row * D);
+  const float xv = x[idx], zv = z != nullptr ? z[idx] : 0.f;
+  const float score = score_of(eps[row * ld_eps + e], std_div);
+  float xm, xn;
+  if (kind == ZEDO_UPD_ANCESTRAL_VP) {
+    xm = __fdiv_rn(__fadd_rn(xv, __fmul_rn(p0, score)), __fsqrt_rn(__fsub_rn(1.f, p0)));
+    xn = __fadd_rn(xm, __fmul_rn(__fsqrt_rn(p0), zv));
+  } else if (kind == ZEDO_UPD_ANCESTRAL_VE) {
+    const float d2 = __fsub_rn(__fmul_rn(p0, p0), __fmul_rn(p1, p1));
+    xm = __fadd_rn(xv, __fmul_rn(score, d2));
+    const float sd = __fsqrt_rn(__fdiv_rn(__fmul_rn(__fmul_rn(p1, p1), d2), __fmul_rn(p0, p0)));
+    xn = __fadd_rn(xm, __fmul_rn(sd, zv));
+  } else {
+    float base;
+    if (kind == ZEDO_UPD_LANGEVIN) {
+      const float gn = (float)(stats[0] / stats[2]), nn = (float)(stats[1] / stats[2]);
+      base = __fdiv_rn(__fmul_rn(p0, nn), gn);
+    } else {
+      base = __fmul_rn(p0, p2);
+    }
+    const float step = __fmul_rn(__fmul_rn(__fmul_rn(base, base), 2.f), p1);
+    xm = __fadd_rn(xv, __fmul_rn(step, score));
+    xn = __fadd_rn(xm, __fmul_rn(__fsqrt_rn(__fmul_rn(step, 2.f)), zv));
+  }
+  if (x_mean != nullptr) x_mean[idx] = xm;
+  if (x_next != nullptr) x_next[idx] = xn;
+}
+
+int launch_row_norm_stats(const float* eps, int ld_eps, const float* z, float std_div, float* norms, double* stats,
+                          int64_t B, int D, cudaStream_t st) {
+  if (B == 0) return 0;
+  row_norms_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(eps, ld_eps, z, std_div, norms, B, D);
+  ZEDO_LAUNCH_CHECK();
+  norm_stats_kernel<<<1, 1024, 0, st>>>(norms, B, stats);
+  ZEDO_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_noise_update(int kind, const float* x, const float* eps, int ld_eps, const float* z, float std_div,
+                        float p0, float p1, float p2, const double* stats, float* x_next, float* x_mean, int64_t B,
+                        int D, cudaStream_t st) {
+  if (B == 0) return 0;
+  const int64_t n = B * D;
+  noise_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kind, x, eps, ld_eps, z, std_div, p0, p1, p2, stats,
+                                                                x_next, x_mean, B, D);
+  ZEDO_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace zedo

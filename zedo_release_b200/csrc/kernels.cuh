@@ -38,6 +38,11 @@ int launch_grad_field(const float* uv, const float* x, const float* K, float* co
 int launch_pack_x(const float* x, __half* xa, int64_t B, int D, cudaStream_t st);
 int launch_sde_update(const float* x, const float* eps, int ld_eps, const float* z, const SdeCoef& c, int predictor,
                       int probability_flow, float* x_next, float* x_mean, int64_t B, int D, cudaStream_t st);
+int launch_row_norm_stats(const float* eps, int ld_eps, const float* z, float std_div, float* norms, double* stats,
+                          int64_t B, int D, cudaStream_t st);
+int launch_noise_update(int kind, const float* x, const float* eps, int ld_eps, const float* z, float std_div,
+                        float p0, float p1, float p2, const double* stats, float* x_next, float* x_mean, int64_t B,
+                        int D, cudaStream_t st);
 int launch_sgemm_tn(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M,
                     int N, int K, cudaStream_t st, int accumulate = 0);
 int launch_timestep_embedding(const float* tin, const float* freqs, float* emb, int n_steps, int half, int fourier,

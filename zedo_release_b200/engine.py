@@ -19,7 +19,16 @@ GEMM_MODES = {"split3": nat.GEMM_SPLIT3, "split2": nat.GEMM_SPLIT2, "fp16": nat.
               "fp8lo": nat.GEMM_FP8LO}
 
 
+#: GEMM arithmetic used when a call does not name one.  "fp8lo" (fp16 main product + the two low-order products in
+#: e4m3) holds every parity bound at the "split3" level (tests parametrised over both) at two thirds of
+#: its tensor work; a plan whose 1024x1024 weights are too heavy-tailed for it serves the request with the split3
+#: products on its own (zedo_b200.h).
+DEFAULT_MODE = "fp8lo"
+
+
 def _mode(mode) -> int:
+    if mode is None:
+        mode = DEFAULT_MODE
     return GEMM_MODES[mode] if isinstance(mode, str) else int(mode)
 
 
@@ -79,7 +88,7 @@ class ScorePlan:
         self.capacity = int(nat.lib.zedo_plan_capacity(self._h))
 
     @_device_scoped
-    def reserve(self, max_steps: int, mode="split3") -> None:
+    def reserve(self, max_steps: int, mode=None) -> None:
         """Size the per-step bias tables (and the FP32-mode workspaces) now, so no later call allocates."""
         nat.check(nat.lib.zedo_plan_reserve(self._h, int(max_steps), _mode(mode), _stream()), "zedo_plan_reserve")
 
@@ -111,7 +120,7 @@ class ScorePlan:
 
     # -- ScoreModelFC_Adv.forward (model.py:215-298) --------------------------------------------
     @_device_scoped
-    def forward(self, x: torch.Tensor, t999: float, mode="split3") -> torch.Tensor:
+    def forward(self, x: torch.Tensor, t999: float, mode=None) -> torch.Tensor:
         x = _f32(x, "x")
         B = x.shape[0]
         out = torch.empty_like(x)
@@ -123,7 +132,7 @@ class ScorePlan:
     @_device_scoped
     def sde_step(self, x: torch.Tensor, t: float, z: Optional[torch.Tensor] = None, predictor: str = "euler_maruyama",
                  probability_flow: bool = True, beta_min: float = 0.1, beta_max: float = 20.0, n_scales: int = 1000,
-                 mode="split3") -> Tuple[torch.Tensor, torch.Tensor]:
+                 mode=None) -> Tuple[torch.Tensor, torch.Tensor]:
         x = _f32(x, "x")
         if z is not None:
             z = _f32(z, "z")
@@ -134,12 +143,45 @@ class ScorePlan:
                                         x.shape[0], _mode(mode), _stream()), "zedo_sde_step")
         return x_next, x_mean
 
+    # -- noise-bearing predictors / correctors with injected noise (sampling.py:208-324) ---------------------
+    UPDATE_KINDS = {"ancestral_vp": nat.UPD_ANCESTRAL_VP, "ancestral_ve": nat.UPD_ANCESTRAL_VE,
+                    "langevin": nat.UPD_LANGEVIN, "ald": nat.UPD_ALD}
+
+    @_device_scoped
+    def score_stats(self, x: torch.Tensor, label: float, z: Optional[torch.Tensor] = None, std_div: float = 0.0,
+                    want_stats: bool = False, mode=None) -> Optional[torch.Tensor]:
+        """Network forward with time label ``label`` (the output stays in the plan for ``noise_update``); with
+        ``want_stats`` returns the device float64 vector (sum_rows |score_row|, sum_rows |z_row|, rows) of this
+        shard -- all-reduce it (SUM) over the ranks to make the Langevin step size global (sampling.py:281-283)."""
+        x = _f32(x, "x")
+        stats = torch.empty((3,), dtype=torch.float64, device=x.device) if want_stats else None
+        if want_stats:
+            z = _f32(z, "z")
+        nat.check(nat.lib.zedo_score_stats(self._h, _ptr(x), float(label), _ptr(z), float(std_div), _ptr(stats),
+                                           x.shape[0], _mode(mode), _stream()), "zedo_score_stats")
+        return stats
+
+    @_device_scoped
+    def noise_update(self, kind: str, x: torch.Tensor, z: Optional[torch.Tensor], std_div: float, p0: float,
+                     p1: float = 0.0, p2: float = 0.0, stats: Optional[torch.Tensor] = None
+                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(x_next, x_mean) of one ancestral / Langevin / ALD update from the network output of the preceding
+        ``score_stats`` call (see include/zedo_b200.h for p0..p2)."""
+        x = _f32(x, "x")
+        if z is not None:
+            z = _f32(z, "z")
+        x_next, x_mean = torch.empty_like(x), torch.empty_like(x)
+        nat.check(nat.lib.zedo_noise_update(self._h, self.UPDATE_KINDS[kind], _ptr(x), _ptr(z), float(std_div),
+                                            float(p0), float(p1), float(p2), _ptr(stats), _ptr(x_next), _ptr(x_mean),
+                                            x.shape[0], _stream()), "zedo_noise_update")
+        return x_next, x_mean
+
     # -- the OIL loop (run/opt_main.py:202-220) ------------------------------------------------------
     @_device_scoped
     def oil_loop(self, x: torch.Tensor, T: torch.Tensor, uv: torch.Tensor, K: torch.Tensor,
                  conf: Optional[torch.Tensor], t_sched: Sequence[float], phase_switch: Optional[int] = None,
                  dump_steps: Iterable[int] = (), beta_min: float = 0.1, beta_max: float = 20.0, n_scales: int = 1000,
-                 mode="split3") -> Optional[torch.Tensor]:
+                 mode=None) -> Optional[torch.Tensor]:
         """In place on ``x`` [B,J,3] and ``T`` [B,3] (and clamps ``conf`` in place like the
         reference).  Returns the dump tensor [n_dump,B,J,3] or None."""
         for name, t in (("x", x), ("T", T), ("uv", uv), ("K", K)):
@@ -318,7 +360,7 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
 # -- the whole per-hypothesis pipeline (run/opt_main.py:166-222) ------------------------------------------
 @_device_scoped
 def run_pose_optimisation(plan: ScorePlan, db_2d: torch.Tensor, K: torch.Tensor, clusters: torch.Tensor, cfg: dict,
-                          hypo: int = 1, mode="split3", t_start: float = 0.1, b_global: Optional[int] = None,
+                          hypo: int = 1, mode=None, t_start: float = 0.1, b_global: Optional[int] = None,
                           steps: Optional[int] = None, phase_switch: Optional[int] = None,
                           pelvis: Tuple[int, int] = (0, 0), ray_init: bool = False, use_conf: bool = True,
                           root_relative: bool = True, per_hypothesis_cluster: bool = True) -> torch.Tensor:

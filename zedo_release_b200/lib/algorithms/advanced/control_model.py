@@ -85,7 +85,7 @@ class Control_ScoreModelFC_Adv(nn.Module):
         self.cond_part_mask_prob = config.training.cond_part_mask_prob
         self.cond_joint_mask_prob = config.training.cond_joint_mask_prob
         self._plans = _ControlPlanCache()
-        self.gemm_mode = "split3"
+        self.gemm_mode = engine.DEFAULT_MODE
         self.init_weight()
 
     def init_weight(self):

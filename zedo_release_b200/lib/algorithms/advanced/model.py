@@ -112,7 +112,7 @@ class ScoreModelFC_Adv(nn.Module):
         self.cond_part_mask_prob = config.training.cond_part_mask_prob
         self.cond_joint_mask_prob = config.training.cond_joint_mask_prob
         self._plans = _PlanCache()
-        self.gemm_mode = "split3"
+        self.gemm_mode = engine.DEFAULT_MODE
 
     def zedo_plan(self, batch):
         """The packed plan for a batch of this size (also used by the fused sampler fast path)."""

@@ -14,7 +14,7 @@ import functools
 import numpy as np
 import torch
 
-from zedo_release_b200.parallel import global_batch_mean
+from zedo_release_b200.parallel import global_batch_mean, global_sum_
 from . import sde_lib
 from . import utils as mutils
 from .utils import from_flattened_numpy, to_flattened_numpy, get_score_fn  # noqa: F401
@@ -114,6 +114,30 @@ class ReverseDiffusionPredictor(Predictor):
         return x_mean + G[:, None, None] * z, x_mean
 
 
+def _fused_score(score_fn, x, t):
+    """The pieces of a fused update, or None when the eager composition has to serve the call: the packed plan of
+    the network behind ``score_fn``, the time label and the std divisor of get_score_fn (utils.py:751-795) for a
+    batch-uniform time.  Float32 scalars are formed on the host exactly as the reference forms them on tensors."""
+    info = getattr(score_fn, "zedo", None)
+    if info is None or info["train"] or not hasattr(info["model"], "zedo_plan") or not x.is_cuda:
+        return None
+    sde, model, continuous = info["sde"], info["model"], info["continuous"]
+    if getattr(model.config.model, "scale_by_sigma", False) or not bool((t == t[0]).all()):
+        return None
+    t0 = t[:1].detach().cpu().float()
+    if isinstance(sde, (sde_lib.VPSDE, sde_lib.subVPSDE)):
+        if not (continuous or isinstance(sde, sde_lib.subVPSDE)):
+            return None  # discrete VP labels: not a shipped configuration
+        label = float((t0 * 999)[0])
+        std_div = float(sde.marginal_prob(torch.zeros(1, 1, 1), t0)[1][0])
+    elif isinstance(sde, sde_lib.VESDE) and continuous:
+        label = float(sde.marginal_prob(torch.zeros(1, 1, 1), t0)[1][0])
+        std_div = 0.0
+    else:
+        return None
+    return model.zedo_plan(x.shape[0]), label, std_div, t0, getattr(model, "gemm_mode", None)
+
+
 @register_predictor(name='ancestral_sampling')
 class AncestralSamplingPredictor(Predictor):
     """Ancestral sampling; VE/VP SDEs only, no probability flow (sampling.py:208-244)."""
@@ -126,6 +150,17 @@ class AncestralSamplingPredictor(Predictor):
 
     def update_fn(self, x, t, condition, mask):
         sde = self.sde
+        fused = _fused_score(self.score_fn, x, t)
+        if fused is not None:  # network forward + one fused update kernel, noise injected by the caller's RNG
+            plan, label, std_div, t0, mode = fused
+            ts = (t0 * (sde.N - 1) / sde.T).long()
+            noise = torch.randn_like(x)
+            plan.score_stats(x, label, std_div=std_div, mode=mode)
+            if isinstance(sde, sde_lib.VESDE):
+                sigma = sde.discrete_sigmas[ts]
+                adjacent = torch.where(ts == 0, torch.zeros_like(t0), sde.discrete_sigmas[ts - 1])
+                return plan.noise_update("ancestral_ve", x, noise, std_div, float(sigma[0]), float(adjacent[0]))
+            return plan.noise_update("ancestral_vp", x, noise, std_div, float(sde.discrete_betas[ts][0]))
         timestep = (t * (sde.N - 1) / sde.T).long()
         score = self.score_fn(x, t, condition, mask)
         noise = torch.randn_like(x)
@@ -175,6 +210,16 @@ class LangevinCorrector(Corrector):
     def update_fn(self, x, t, condition, mask):
         alpha = _langevin_alpha(self.sde, t)
         x_mean = x
+        fused = _fused_score(self.score_fn, x, t)
+        if fused is not None:
+            plan, label, std_div, t0, mode = fused
+            a0 = float(_langevin_alpha(self.sde, t0)[0])
+            for _ in range(self.n_steps):
+                noise = torch.randn_like(x)
+                stats = plan.score_stats(x, label, z=noise, std_div=std_div, want_stats=True, mode=mode)
+                global_sum_(stats)  # batch means over ALL ranks when the poses are sharded (one 3-double all_reduce)
+                x, x_mean = plan.noise_update("langevin", x, noise, std_div, self.snr, a0, stats=stats)
+            return x, x_mean
         for _ in range(self.n_steps):
             grad = self.score_fn(x, t, condition, mask)
             noise = torch.randn_like(x)
@@ -199,6 +244,16 @@ class AnnealedLangevinDynamics(Corrector):
         alpha = _langevin_alpha(self.sde, t)
         std = self.sde.marginal_prob(x, t)[1]
         x_mean = x
+        fused = _fused_score(self.score_fn, x, t)
+        if fused is not None:
+            plan, label, std_div, t0, mode = fused
+            a0 = float(_langevin_alpha(self.sde, t0)[0])
+            std_m = float(self.sde.marginal_prob(torch.zeros(1, 1, 1), t0)[1][0])
+            for _ in range(self.n_steps):
+                noise = torch.randn_like(x)
+                plan.score_stats(x, label, std_div=std_div, mode=mode)
+                x, x_mean = plan.noise_update("ald", x, noise, std_div, self.snr, a0, std_m)
+            return x, x_mean
         for _ in range(self.n_steps):
             grad = self.score_fn(x, t, condition, mask)
             noise = torch.randn_like(x)
@@ -265,7 +320,7 @@ def get_pc_sampler(sde, shape, predictor, corrector, inverse_scaler, snr, n_step
                 x, x_mean = plan.sde_step(x, float(t_val), z=z, predictor=_FUSED_PREDICTORS[predictor],
                                           probability_flow=probability_flow, beta_min=sde.beta_0,
                                           beta_max=sde.beta_1, n_scales=sde.N,
-                                          mode=getattr(model, "gemm_mode", "split3"))
+                                          mode=getattr(model, "gemm_mode", None))
             else:
                 mask = torch.ones_like(x) * 0
                 vec_t = torch.ones(batch_size, device=t_val.device) * t_val

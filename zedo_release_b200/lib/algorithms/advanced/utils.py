@@ -72,6 +72,8 @@ def get_score_fn(sde, model, train=False, continuous=False):
             return model_fn(x, labels, condition, mask)
     else:
         raise NotImplementedError(f"SDE class {sde.__class__.__name__} not yet supported.")
+    # what the fused update kernels need to know about this closure (sampling.py of the mirror)
+    score_fn.zedo = dict(sde=sde, model=model, continuous=continuous, train=train)
     return score_fn
 
 

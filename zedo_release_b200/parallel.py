@@ -66,7 +66,16 @@ def global_batch_mean(per_pose: torch.Tensor) -> torch.Tensor:
     return (acc[0] / acc[1]).to(per_pose.dtype)
 
 
-def run_sharded(plan_or_factory, db_2d, K, clusters, cfg, hypo=1, mode="split3", gt=None, protocol2=False,
+def global_sum_(stats: torch.Tensor) -> torch.Tensor:
+    """In-place SUM all_reduce of a small device vector over the ranks (no-op in a single process): the
+    (sum |score_row|, sum |z_row|, rows) statistics ``ScorePlan.score_stats`` returns become global, so the fused
+    Langevin update uses the batch means of the WHOLE batch (reference sampling.py:281-283)."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    return stats
+
+
+def run_sharded(plan_or_factory, db_2d, K, clusters, cfg, hypo=1, mode=None, gt=None, protocol2=False,
                 actions=None, local_shard=False, n_total=None, gather_results=True, **run_kw):
     """The whole job on this rank's shard: slice the (host) arrays by ``shard_range``, copy the shard to the device,
     run IPO + OIL (IPO gradients scaled by the GLOBAL batch: the reference's loss is a mean over the whole batch,
