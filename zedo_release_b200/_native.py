@@ -11,7 +11,8 @@ import os
 from typing import Dict, Iterable, Sequence
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzedo_b200.so")
+# ZEDO_B200_LIB: load another build of the same sources (tools/: the -DZEDO_EXPERIMENTS=1 timing build); never a non-CUDA path
+LIB_PATH = os.environ.get("ZEDO_B200_LIB") or os.path.join(_HERE, "libzedo_b200.so")
 
 GEMM_SPLIT3, GEMM_FP16, GEMM_FP32, GEMM_SPLIT2, GEMM_FP8LO = 0, 1, 2, 3, 4
 NET_SCORE_FC_ADV, NET_CONTROL = 0, 1

@@ -21,6 +21,8 @@ struct LayerArgs {
   int dbg;  // timing experiments only (env ZEDO_DBG): 1 = no bulk copies after the first fill, 2 = no MMAs
   int a_fmt;  // block format of A (common.cuh): 0 = [hi16 | lo16], 1 = [hi16 | hi8 | lo8 | lo16]
   int o_fmt;  // block format of out / resid / addend
+  int o_flags;  // format-1 output: bit 0 = some consumer reads the e4m3 images (hi8, lo8), bit 1 = some consumer reads
+                // lo16 (residual / addend epilogue, post_dense); images nobody reads are neither formed nor stored
 };
 // a short host-side index list (IPO key joints, evaluated joint subset) travels by value in the kernel parameters:
 // no device allocation or copy per call (n = 0: "no list")

@@ -148,6 +148,19 @@ layer_tc2_kernel(const LayerArgs args) {
             }
             continue;
           }
+          if (ZEDO_EXPERIMENTS && (args.dbg & 4)) {
+            // experiment: 3/4 of the stage bytes cross L2 -> SMEM (what a stage without the hi8 images would cost);
+            // results are garbage by design
+            mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes / 4 * 3);
+            bulk_g2s(sA + stage * Cfg::kABytes, a_src + (int64_t)kb * a_blk, Cfg::kABytes / 4 * 3, &full[stage]);
+            bulk_g2s(sB + stage * Cfg::kBBytes, w_src + (int64_t)kb * 2 * (Cfg::kHalfN * kBlockK), Cfg::kBBytes / 4 * 3,
+                     &full[stage]);
+            if (++stage == S) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
           bulk_g2s(sA + stage * Cfg::kABytes, a_src + (int64_t)kb * a_blk, Cfg::kABytes, &full[stage]);
           bulk_g2s(sB + stage * Cfg::kBBytes, w_src + (int64_t)kb * 2 * (Cfg::kHalfN * kBlockK), Cfg::kBBytes,
@@ -245,7 +258,8 @@ layer_tc2_kernel(const LayerArgs args) {
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      epilogue_tile<BN, EPI, EW>(args, tmem_base + (uint32_t)(as * BN), q, chalf, r, mt, nt);
+      if (!(ZEDO_EXPERIMENTS && (args.dbg & 8)))  // experiment bit 8: no epilogue work at all (feed + MMA only)
+        epilogue_tile<BN, EPI, EW>(args, tmem_base + (uint32_t)(as * BN), q, chalf, r, mt, nt);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[as], 0);  // the leader's MMA lane owns accumulator reuse

@@ -313,7 +313,8 @@ __device__ __forceinline__ void epilogue_tile(const LayerArgs& args, uint32_t tm
       }
     } else {
       // format 1: hi16, lo16 as above plus the e4m3 images hi8 = e4m3(hi16), lo8 = e4m3(lo16 * 2^11); one 16-byte
-      // chunk of an 8-bit image holds 16 columns of this row
+      // chunk of an 8-bit image holds 16 columns of this row.  Only the images a later layer reads are produced.
+      const bool want8 = (args.o_flags & 1) != 0, want_lo = (args.o_flags & 2) != 0;
       uint8_t* blk8 = reinterpret_cast<uint8_t*>(args.out + ((int64_t)mt * nkb_out + kbo) * kBlk) + r * 16;
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj) {
@@ -326,16 +327,21 @@ __device__ __forceinline__ void epilogue_tile(const LayerArgs& args, uint32_t tm
           for (int e = 0; e < 4; ++e) split_pair(v[8 * j + 2 * e], v[8 * j + 2 * e + 1], hi[e], lo[e]);
           const int pc = (hsel * 4 + j) * kChunkStride;
           *reinterpret_cast<uint4*>(args.out + row_off + pc) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(args.out + row_off + kLoOff + pc) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          if (want_lo)
+            *reinterpret_cast<uint4*>(args.out + row_off + kLoOff + pc) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          if (want8) {
 #pragma unroll
-          for (int w = 0; w < 2; ++w) {
-            h8[2 * j2 + w] = half2x2_to_e4m3x4(hi[2 * w], hi[2 * w + 1], false);
-            l8[2 * j2 + w] = half2x2_to_e4m3x4(lo[2 * w], lo[2 * w + 1], true);
+            for (int w = 0; w < 2; ++w) {
+              h8[2 * j2 + w] = half2x2_to_e4m3x4(hi[2 * w], hi[2 * w + 1], false);
+              l8[2 * j2 + w] = half2x2_to_e4m3x4(lo[2 * w], lo[2 * w + 1], true);
+            }
           }
         }
-        const int pc8 = (hsel * 2 + jj) * (kActTileRows * 16);
-        *reinterpret_cast<uint4*>(blk8 + kHi8ByteOff + pc8) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
-        *reinterpret_cast<uint4*>(blk8 + kLo8ByteOff + pc8) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
+        if (want8) {
+          const int pc8 = (hsel * 2 + jj) * (kActTileRows * 16);
+          *reinterpret_cast<uint4*>(blk8 + kHi8ByteOff + pc8) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+          *reinterpret_cast<uint4*>(blk8 + kLo8ByteOff + pc8) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
+        }
       }
     }
   }
