@@ -153,6 +153,18 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
       : "memory");
 }
 
+// The same without release semantics: used by the epilogue warps to hand an accumulator back to the MMA lane.  What
+// that hand-over has to order are the warp's TMEM reads (tcgen05.wait::ld + tcgen05.fence::before_thread_sync), not its
+// global stores -- a releasing arrive makes the warp wait (MEMBAR) until every store of the tile has drained.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+
 // hi/lo split of two floats with packed conversions (F2FP.PACK_AB instead of two F2F)
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(a, b);
