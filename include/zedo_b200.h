@@ -223,6 +223,17 @@ int zedo_pck_counts(const float* pred, const double* gt, const int32_t* select, 
  * poses and joints per coordinate. */
 int zedo_hypothesis_std(const float* pred, int64_t N, int32_t S, int32_t J, double* out_std, void* stream);
 
+/* ---- cluster-pose generation -------------------------------------------------------------------------
+ * Produces what the drivers load from clusters/{h36m,3dhp}_cluster{S}.npy (run/opt_main.py:58-65): S centres of
+ * Lloyd's k-means over training poses.  The reference ships the files, not their generator (run/opt_main_infant.py:25,34
+ * only imports scipy.cluster.vq / sklearn KMeans).  x [N, D] float32 (D = 3 J flattened poses), centers [S, D] float32
+ * in/out (initial centres in, fitted centres out), assign [N] int32 out (label under the final centres), dist [N]
+ * float64 out (nullable; squared distance to the assigned centre).  `iters` Lloyd iterations; distances and sums in
+ * float64 with a fixed summation order (bit-reproducible); ties go to the lowest centre index; an empty cluster keeps
+ * its centre. */
+int zedo_kmeans_fit(const float* x, int64_t N, int32_t D, int32_t S, int32_t iters, float* centers,
+                    int32_t* assign, double* dist, void* stream);
+
 /* ---- misc ---------------------------------------------------------------------------------------- */
 const char* zedo_strerror(int code);
 int zedo_abi_version(void);

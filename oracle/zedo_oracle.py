@@ -757,6 +757,29 @@ _H36M_TEMPLATE = np.array([
     [-0.32, 0.04, 0.00]], dtype=f32)  # metres, y down (camera frame), root = pelvis
 
 
+def kmeans_lloyd(x, init_centres, iters):
+    """Lloyd's k-means as the cluster-file generator runs it (zedo_release_b200/clusters.py; the reference ships the
+    cluster files, not their generator -- run/opt_main.py:58-65 loads them, run/opt_main_infant.py:25,34 only imports
+    scipy.cluster.vq / sklearn KMeans).  x [N, D] float32, float64 distances and means, ties to the lowest index,
+    an empty cluster keeps its centre.  Returns (centres [S, D] float32, labels [N], squared distances [N] float64)."""
+    x64 = x.astype(np.float64)
+    c = init_centres.astype(f32).copy()
+
+    def assign(c):
+        d = ((x64[:, None, :] - c.astype(np.float64)[None]) ** 2).sum(-1)
+        lab = d.argmin(1)
+        return lab, d[np.arange(len(x)), lab]
+
+    for _ in range(iters):
+        lab, _ = assign(c)
+        for k in range(len(c)):
+            m = lab == k
+            if m.any():
+                c[k] = x64[m].mean(0).astype(f32)
+    lab, dist = assign(c)
+    return c, lab.astype(np.int32), dist
+
+
 def skeleton_template(n_joints=17):
     if n_joints == 17:
         return _H36M_TEMPLATE.copy()

@@ -689,3 +689,39 @@ def test_duplicate_dump_steps_are_served(zr, plan17, golden):
                                C.c_void_p(dev(K).data_ptr()), None, nat.f32_array(ts), 6, 2, 0.1, 20.0, 1000,
                                C.c_void_p(d.data_ptr()), nat.i32_array([1, 1]), 2, 16, 0, None)
     assert rc == -1
+
+
+# ---- cluster-pose generation (k-means) ----------------------------------------------------------------------------
+def test_kmeans_cluster_generation(zr, tmp_path):
+    """zedo_kmeans_fit against the numpy restatement: same initial centres -> same labels, centres to float32 rounding;
+    the written file is what run/opt_main.py:59 loads; reproducible bit for bit."""
+    from zedo_release_b200 import clusters as zc
+    rng = np.random.default_rng(4)
+    base = zo.make_synthetic_dataset(8, seed=2, n_clusters=8)["clusters"]          # 8 well separated modes
+    poses = (base[rng.integers(0, 8, 5000)] + rng.normal(0, 0.02, (5000, 17, 3))).astype(np.float32)
+    S, iters = 8, 12
+    c_gpu, lab_gpu, d_gpu = zc.kmeans_clusters(dev(poses), S, iters=iters, seed=3)
+    x = (poses - poses[:, 0:1]).reshape(5000, 51)
+    c_or, lab_or, d_or = zo.kmeans_lloyd(x, x[zc.initial_centres(5000, S, 3)], iters)
+    assert np.array_equal(lab_gpu.cpu().numpy(), lab_or)
+    assert rel_err(c_gpu.cpu().numpy().reshape(S, 51), c_or) < 1e-6
+    assert np.allclose(d_gpu.cpu().numpy(), d_or, rtol=1e-9, atol=1e-12)
+    c2, lab2, _ = zc.kmeans_clusters(dev(poses), S, iters=iters, seed=3)
+    assert torch.equal(c2, c_gpu) and torch.equal(lab2, lab_gpu)
+    path = str(tmp_path / f"h36m_cluster{S}.npy")
+    zc.save_cluster_file(path, c_gpu)
+    loaded = np.load(path)
+    assert loaded.dtype == np.float32 and loaded.shape == (S, 17, 3) and np.abs(loaded[:, 0]).max() == 0.0
+    # every recovered centre sits on one of the generating modes (root-relative), and all modes are found
+    modes = (base - base[:, 0:1]).reshape(8, 51)
+    nearest = ((loaded.reshape(S, 1, 51) - modes[None]) ** 2).sum(-1).argmin(1)
+    assert sorted(nearest.tolist()) == list(range(8)) or len(set(nearest.tolist())) >= 6  # Lloyd may merge a pair
+    # the generated file drives the pipeline like a shipped one
+    ds = zo.make_synthetic_dataset(64, seed=9)
+    plan = zr.ScorePlan(zo.make_weights(seed=0), n_joints=17, max_batch=64 * S, device=0)
+    cfg = dict(zo.H36M_ZEDO_CFG)
+    cfg["OIL_iterations"] = 10
+    cfg["IPO_iterations"] = 5
+    res = zr.run_pose_optimisation(plan, dev(ds["db_2d"]), dev(ds["camera_param"]), dev(loaded), cfg, hypo=S)
+    plan.close()
+    assert res.shape == (64, S, 17, 3) and bool(torch.isfinite(res).all())

@@ -359,3 +359,26 @@ def test_checkpoint_file_in_the_reference_format(lib, golden, tmp_path):
     out2 = plan.forward(torch.tensor(g["x"], device="cuda"), 99.9)
     plan.close()
     assert torch.equal(out2, out)
+
+
+def test_custom_dataset_read_data_and_eval(lib, tmp_path):
+    """lib/dataset/custom.py: the reference's TODO ``read_data`` filled in (npz with 2D + confidence, optional 3D, K,
+    image names), same constructor / attributes / eval_multi contract as run/inference.py:118-127,236-237 uses; the
+    printed numbers equal the reference's own CustomDataset.eval_multi on the same arrays (numpy restatement)."""
+    from lib.dataset.custom import CustomDataset
+    ds = zo.make_synthetic_dataset(40, seed=21, n_clusters=2)
+    np.savez(tmp_path / "custom.npz", keypoints_2d=ds["db_2d"], keypoints_3d=ds["db_3d"] + ds["root"][:, None],
+             camera_params=ds["camera_param"])
+    d = CustomDataset(str(tmp_path), sample_interval=2)
+    assert len(d) == 20 and d.db_2d.shape == (20, 17, 3) and d.camera_param.shape == (20, 3, 3) and len(d.image_name) == 20
+    rng = np.random.default_rng(0)
+    preds = ((d.db_3d - d.db_3d[:, 0:1])[:, None] + rng.normal(0, 0.02, (20, 3, 17, 3))).astype(np.float32)
+    for p2 in (False, True):
+        got = d.eval_multi(preds, protocol2=p2, print_verbose=True)
+        _, e_or, _ = zo.eval_multi(preds.astype(np.float64), (d.db_3d - d.db_3d[:, 0:1]).astype(np.float64), protocol2=p2)
+        assert abs(got - float(np.mean(e_or))) < 1e-7
+    # inference-only use: no 3D labels, a single K, no confidence column
+    w = CustomDataset.from_arrays(ds["db_2d"][:, :, :2], ds["camera_param"][0])
+    assert w.db_3d.shape == (40, 17, 3) and not w.db_3d.any() and np.all(w.db_2d[:, :, 2] == 1)
+    with pytest.raises(ValueError):
+        CustomDataset.from_arrays(ds["db_2d"][:, :, :1], ds["camera_param"])

@@ -182,3 +182,14 @@ def test_noise_bearing_updates_vp_ve(golden):
                      ("lang", zo.langevin_update_vp(W, x, t, zs, snr=0.16, n_steps=2)),
                      ("ald", zo.langevin_update_vp(W, x, t, zs, snr=0.16, n_steps=1, ald=True))):
         assert rel_err(got[0], g[f"{tag}_x"]) < 5e-6 and rel_err(got[1], g[f"{tag}_mean"]) < 5e-6, tag
+
+
+def test_kmeans_restatement_recovers_planted_clusters():
+    """The numpy k-means the CUDA cluster generator is checked against (oracle/zedo_oracle.py: kmeans_lloyd)."""
+    rng = np.random.default_rng(0)
+    modes = rng.normal(0, 1.0, (5, 12)).astype(np.float32)
+    lab_true = rng.integers(0, 5, 800)
+    x = (modes[lab_true] + rng.normal(0, 0.01, (800, 12))).astype(np.float32)
+    first = [int(np.flatnonzero(lab_true == k)[0]) for k in range(5)]
+    c, lab, dist = zo.kmeans_lloyd(x, x[first], 5)
+    assert np.array_equal(lab, lab_true) and np.abs(c - modes).max() < 5e-3 and dist.max() < 12 * 0.05 ** 2

@@ -27,7 +27,7 @@ EXPORTS = (
     "zedo_eval_multi", "zedo_strerror", "zedo_abi_version", "zedo_launch_count", "zedo_subvp_scalars",
     "zedo_blocked_offset", "zedo_plan_profile", "zedo_plan_profile_read", "zedo_ipo_fit_ex", "zedo_pck_counts",
     "zedo_hypothesis_std", "zedo_plan_reserve", "zedo_set_option", "zedo_get_option", "zedo_score_stats",
-    "zedo_noise_update",
+    "zedo_noise_update", "zedo_kmeans_fit",
 )
 
 
@@ -74,6 +74,7 @@ def _load() -> C.CDLL:
         "zedo_eval_multi": (C.c_int, [p, p, i32, i64, i32, i32, C.POINTER(i32), i32, p, p, p, p, vp]),
         "zedo_pck_counts": (C.c_int, [p, p, p, i64, i32, i32, C.POINTER(i32), i32, p, vp]),
         "zedo_hypothesis_std": (C.c_int, [p, i64, i32, i32, p, vp]),
+        "zedo_kmeans_fit": (C.c_int, [p, i64, i32, i32, i32, p, p, p, vp]),
         "zedo_strerror": (C.c_char_p, [C.c_int]),
         "zedo_abi_version": (C.c_int, []),
         "zedo_launch_count": (i64, []),

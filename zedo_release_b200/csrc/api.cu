@@ -1161,6 +1161,14 @@ int zedo_pck_counts(const float* pred, const double* gt, const int32_t* select, 
   return launch_pck_counts(pred, gt, select, N, S, J, sub, (unsigned long long*)counts, st);
 }
 
+int zedo_kmeans_fit(const float* x, int64_t N, int32_t D, int32_t S, int32_t iters, float* centers, int32_t* assign,
+                    double* dist, void* stream) {
+  if (N == 0 || S == 0) return 0;
+  if (!x || !centers || !assign) return ZEDO_E_INVALID;
+  if (N < 0 || D < 1 || D > 256 || S < 1 || S > 4096 || iters < 0 || iters > 100000) return ZEDO_E_SHAPE;
+  return launch_kmeans(x, N, D, S, iters, centers, assign, dist, (cudaStream_t)stream);
+}
+
 int zedo_hypothesis_std(const float* pred, int64_t N, int32_t S, int32_t J, double* out_std, void* stream) {
   if (N == 0 || J == 1) return 0;
   if (!pred || !out_std) return ZEDO_E_INVALID;

@@ -2,19 +2,13 @@
 //
 // Restates eval_multi (lib/dataset/h36m.py:394-417, pw3d.py:303-338) and align_to_gt / procrustes
 // (lib/utils/transforms.py:42-148: scaling=True, reflection='best', i.e. NO determinant fix, so
-// reflections are allowed).  One warp per pose, lane j owns joint j, the S hypotheses are a serial
-// loop so "first minimum wins" exactly like np.argmin.  Float64 throughout: the reference's
+// reflections are allowed).  One thread per pose, the S hypotheses are a serial loop so "first
+// minimum wins" exactly like np.argmin.  Float64 throughout: the reference's
 // numpy path promotes to float64 (gt comes from a float64 pickle), and the selection indices
 // have to be bit-exact.
 #include "kernels.cuh"
 
 namespace zedo {
-
-__device__ __forceinline__ double warp_sum_d(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 // One-sided Jacobi SVD of a 3x3 matrix M (row-major): on exit the columns of M are U_i * s_i and
 // V accumulates the right rotations, M_in = U diag(s) V^T.
@@ -49,59 +43,79 @@ __device__ void svd3x3_onesided(double* M, double* V) {
   }
 }
 
+// One THREAD per pose: the S hypotheses are a serial loop in that thread ("first minimum wins" exactly like np.argmin)
+// and every lane of a warp runs its OWN 3x3 SVD on different data.  (The first version gave a pose to a warp with one
+// joint per lane; all 32 lanes then repeated the same float64 Jacobi SVD.)  pred / gt rows are re-read per pass from
+// L1: a warp's 32 poses touch 32 x 3J floats, which the first pass leaves resident.
 __global__ void __launch_bounds__(128)
 eval_multi_kernel(const float* __restrict__ pred, const double* __restrict__ gt, int protocol2, int64_t N, int S,
                   int J, const IntList subset, double* __restrict__ err_min,
                   int* __restrict__ argmin, double* __restrict__ err_all, double* __restrict__ aligned) {
-  const int lane = threadIdx.x & 31;
-  const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
-  const bool active = lane < J;
   // joints that count in the mean: all J, or the listed subset (e.g. the 12 SyRIP joints)
-  bool counted = active;
+  uint32_t counted = J >= 32 ? 0xffffffffu : ((1u << J) - 1u);
   int n_counted = J;
   if (subset.n > 0) {
-    counted = false;
-    for (int i = 0; i < subset.n; ++i) counted |= (subset.v[i] == lane);
+    counted = 0;
+    for (int i = 0; i < subset.n; ++i) counted |= 1u << subset.v[i];
     n_counted = subset.n;
   }
-  double g0 = 0, g1 = 0, g2 = 0;
-  if (active) {
-    g0 = gt[(n * J + lane) * 3 + 0];
-    g1 = gt[(n * J + lane) * 3 + 1];
-    g2 = gt[(n * J + lane) * 3 + 2];
-  }
+  const double* g = gt + n * J * 3;
   // gt statistics for Procrustes (transforms.py:74-85)
   const double invJ = 1.0 / J;
-  const double am0 = warp_sum_d(g0) * invJ, am1 = warp_sum_d(g1) * invJ, am2 = warp_sum_d(g2) * invJ;
-  const double a0 = active ? g0 - am0 : 0, a1 = active ? g1 - am1 : 0, a2 = active ? g2 - am2 : 0;
-  const double a_norm = sqrt(warp_sum_d(a0 * a0 + a1 * a1 + a2 * a2));
+  double am0 = 0, am1 = 0, am2 = 0, a_norm = 0;
+  if (protocol2) {
+    for (int j = 0; j < J; ++j) {
+      am0 += g[3 * j];
+      am1 += g[3 * j + 1];
+      am2 += g[3 * j + 2];
+    }
+    am0 *= invJ;
+    am1 *= invJ;
+    am2 *= invJ;
+    for (int j = 0; j < J; ++j) {
+      const double a0 = g[3 * j] - am0, a1 = g[3 * j + 1] - am1, a2 = g[3 * j + 2] - am2;
+      a_norm += a0 * a0 + a1 * a1 + a2 * a2;
+    }
+    a_norm = sqrt(a_norm);
+  }
 
   double best = 0.0;
   int best_idx = 0;
   for (int s = 0; s < S; ++s) {
-    double p0 = 0, p1 = 0, p2 = 0;
-    if (active) {
-      const float* pp = pred + ((n * S + s) * J + lane) * 3;
-      p0 = pp[0];
-      p1 = pp[1];
-      p2 = pp[2];
-    }
+    const float* pp = pred + (n * S + s) * J * 3;
+    double k = 1.0, bm0 = 0, bm1 = 0, bm2 = 0, b_norm = 1.0;
+    double Rm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     if (protocol2) {
-      const double bm0 = warp_sum_d(p0) * invJ, bm1 = warp_sum_d(p1) * invJ, bm2 = warp_sum_d(p2) * invJ;
-      double b0 = active ? p0 - bm0 : 0, b1 = active ? p1 - bm1 : 0, b2 = active ? p2 - bm2 : 0;
-      const double b_norm = sqrt(warp_sum_d(b0 * b0 + b1 * b1 + b2 * b2));
-      const double an0 = a0 / a_norm, an1 = a1 / a_norm, an2 = a2 / a_norm;
-      b0 /= b_norm;
-      b1 /= b_norm;
-      b2 /= b_norm;
-      double M[9], V[9];  // M = A0^T B0
-      M[0] = warp_sum_d(an0 * b0); M[1] = warp_sum_d(an0 * b1); M[2] = warp_sum_d(an0 * b2);
-      M[3] = warp_sum_d(an1 * b0); M[4] = warp_sum_d(an1 * b1); M[5] = warp_sum_d(an1 * b2);
-      M[6] = warp_sum_d(an2 * b0); M[7] = warp_sum_d(an2 * b1); M[8] = warp_sum_d(an2 * b2);
+      for (int j = 0; j < J; ++j) {
+        bm0 += (double)pp[3 * j];
+        bm1 += (double)pp[3 * j + 1];
+        bm2 += (double)pp[3 * j + 2];
+      }
+      bm0 *= invJ;
+      bm1 *= invJ;
+      bm2 *= invJ;
+      double bn = 0;
+      for (int j = 0; j < J; ++j) {
+        const double b0 = pp[3 * j] - bm0, b1 = pp[3 * j + 1] - bm1, b2 = pp[3 * j + 2] - bm2;
+        bn += b0 * b0 + b1 * b1 + b2 * b2;
+      }
+      b_norm = sqrt(bn);
+      double M[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, V[9];  // M = A0^T B0 of the normalised, centred point sets
+      for (int j = 0; j < J; ++j) {
+        const double an0 = (g[3 * j] - am0) / a_norm, an1 = (g[3 * j + 1] - am1) / a_norm,
+                     an2 = (g[3 * j + 2] - am2) / a_norm;
+        const double b0 = (pp[3 * j] - bm0) / b_norm, b1 = (pp[3 * j + 1] - bm1) / b_norm,
+                     b2 = (pp[3 * j + 2] - bm2) / b_norm;
+        M[0] += an0 * b0; M[1] += an0 * b1; M[2] += an0 * b2;
+        M[3] += an1 * b0; M[4] += an1 * b1; M[5] += an1 * b2;
+        M[6] += an2 * b0; M[7] += an2 * b1; M[8] += an2 * b2;
+      }
       svd3x3_onesided(M, V);
       // R = V U^T = sum_i v_i u_i^T with u_i = M[:, i] / s_i ; trace(S) = sum_i s_i
-      double Rm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Rm[i] = 0.0;
       double tr = 0.0;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -113,30 +127,37 @@ eval_multi_kernel(const float* __restrict__ pred, const double* __restrict__ gt,
 #pragma unroll
           for (int c = 0; c < 3; ++c) Rm[3 * r + c] += V[3 * r + i] * (M[3 * c + i] * inv);
       }
-      const double k = a_norm * tr;  // Z = A_norm * trace * (B0 R) + A_bar   (transforms.py:113)
-      p0 = k * (b0 * Rm[0] + b1 * Rm[3] + b2 * Rm[6]) + am0;
-      p1 = k * (b0 * Rm[1] + b1 * Rm[4] + b2 * Rm[7]) + am1;
-      p2 = k * (b0 * Rm[2] + b1 * Rm[5] + b2 * Rm[8]) + am2;
+      k = a_norm * tr;  // Z = A_norm * trace * (B0 R) + A_bar   (transforms.py:113)
     }
-    if (aligned != nullptr && active) {  // the pose eval_multi scores (align_to_gt output in protocol 2)
-      double* ap = aligned + ((n * S + s) * J + lane) * 3;
-      ap[0] = p0;
-      ap[1] = p1;
-      ap[2] = p2;
+    double esum = 0.0;
+    for (int j = 0; j < J; ++j) {
+      double p0 = pp[3 * j], p1 = pp[3 * j + 1], p2 = pp[3 * j + 2];
+      if (protocol2) {
+        const double b0 = (p0 - bm0) / b_norm, b1 = (p1 - bm1) / b_norm, b2 = (p2 - bm2) / b_norm;
+        p0 = k * (b0 * Rm[0] + b1 * Rm[3] + b2 * Rm[6]) + am0;
+        p1 = k * (b0 * Rm[1] + b1 * Rm[4] + b2 * Rm[7]) + am1;
+        p2 = k * (b0 * Rm[2] + b1 * Rm[5] + b2 * Rm[8]) + am2;
+      }
+      if (aligned != nullptr) {  // the pose eval_multi scores (align_to_gt output in protocol 2)
+        double* ap = aligned + ((n * S + s) * J + j) * 3;
+        ap[0] = p0;
+        ap[1] = p1;
+        ap[2] = p2;
+      }
+      if ((counted >> j) & 1u) {
+        const double d0 = p0 - g[3 * j], d1 = p1 - g[3 * j + 1], d2 = p2 - g[3 * j + 2];
+        esum += sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+      }
     }
-    const double d0 = p0 - g0, d1 = p1 - g1, d2 = p2 - g2;
-    const double e = counted ? sqrt(d0 * d0 + d1 * d1 + d2 * d2) : 0.0;
-    const double err = warp_sum_d(e) / n_counted;
-    if (err_all != nullptr && lane == 0) err_all[n * S + s] = err;
+    const double err = esum / n_counted;
+    if (err_all != nullptr) err_all[n * S + s] = err;
     if (s == 0 || err < best) {
       best = err;
       best_idx = s;
     }
   }
-  if (lane == 0) {
-    err_min[n] = best;
-    argmin[n] = best_idx;
-  }
+  err_min[n] = best;
+  argmin[n] = best_idx;
 }
 
 // PCK / AUC of MPI-INF-3DHP (utils.py:814-849, used by mpii3dHP.py:480-481): per-joint error (mm) of the
@@ -213,9 +234,8 @@ int launch_eval_multi(const float* pred, const double* gt, int protocol2, int64_
                       const IntList& subset, double* err_min, int* argmin, double* err_all,
                       double* aligned, cudaStream_t st) {
   if (N == 0) return 0;
-  const int warps = 4;
-  eval_multi_kernel<<<(unsigned)((N + warps - 1) / warps), warps * 32, 0, st>>>(pred, gt, protocol2, N, S, J, subset,
-                                                                             err_min, argmin, err_all, aligned);
+  eval_multi_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(pred, gt, protocol2, N, S, J, subset, err_min, argmin,
+                                                              err_all, aligned);
   ZEDO_LAUNCH_CHECK();
   return 0;
 }

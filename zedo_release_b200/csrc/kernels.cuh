@@ -45,6 +45,8 @@ int launch_row_norm_stats(const float* eps, int ld_eps, const float* z, float st
 int launch_noise_update(int kind, const float* x, const float* eps, int ld_eps, const float* z, float std_div,
                         float p0, float p1, float p2, const double* stats, float* x_next, float* x_mean, int64_t B,
                         int D, cudaStream_t st);
+int launch_kmeans(const float* x, int64_t N, int D, int S, int iters, float* centers, int* assign, double* dist,
+                  cudaStream_t st);
 int launch_sgemm_tn(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M,
                     int N, int K, cudaStream_t st, int accumulate = 0);
 int launch_timestep_embedding(const float* tin, const float* freqs, float* emb, int n_steps, int half, int fourier,

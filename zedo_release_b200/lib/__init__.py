@@ -23,7 +23,7 @@ import sys
 _SUBMODULES = ("algorithms", "algorithms.advanced", "algorithms.advanced.sde_lib", "algorithms.advanced.utils",
                "algorithms.advanced.model", "algorithms.advanced.control_model", "algorithms.advanced.sampling",
                "algorithms.advanced.simple_zeroshot_opt", "algorithms.ema", "utils", "utils.transforms",
-               "dataset", "dataset.synthetic")
+               "dataset", "dataset.synthetic", "dataset.custom")
 _PACKAGES = ("", "algorithms", "algorithms.advanced", "utils", "dataset")
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _reference_root = None
