@@ -63,9 +63,22 @@ if os.path.exists(rp):
     hid = [c for c in caps if "layer_tc2_kernel" in c.get("Kernel Name", "")]
     if not hid:
         hid = [c for c in caps if "256, 3, 0" in c.get("Kernel Name", "")]
-    if hid:
-        summary["hidden_layer_dram_bytes_per_launch"] = sum(c["dram__bytes_read.sum"] + c["dram__bytes_write.sum"] for c in hid) / len(hid)
-        summary["hidden_layer_tensor_pipe_active_pct"] = sum(c["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"] for c in hid) / len(hid)
+    # keep the figures of the mode that was not captured this time (bench.py reads one key per GEMM mode)
+    prev_path = os.path.join(out_dir, "ncu_summary.json")
+    if os.path.exists(prev_path):
+        prev = json.load(open(prev_path))
+        for k in ("hidden_layer_dram_bytes_per_launch", "hidden_layer_tensor_pipe_active_pct",
+                  "hidden_layer_fp8lo_dram_bytes_per_launch", "hidden_layer_fp8lo_tensor_pipe_active_pct",
+                  "hidden_layer_fp8lo_l2_to_sm_bytes_per_launch"):
+            if k in prev:
+                summary[k] = prev[k]
+    for tagk, sel in (("", "layer_tc2_kernel<3,"), ("fp8lo_", "layer_tc2_kernel<4,")):
+        h = [c for c in hid if sel in c.get("Kernel Name", "")]
+        if h:
+            summary[f"hidden_layer_{tagk}dram_bytes_per_launch"] = sum(c["dram__bytes_read.sum"] + c["dram__bytes_write.sum"] for c in h) / len(h)
+            summary[f"hidden_layer_{tagk}tensor_pipe_active_pct"] = sum(c["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"] for c in h) / len(h)
+            if "l1tex__m_xbar2l1tex_read_bytes.sum" in h[0]:
+                summary[f"hidden_layer_{tagk}l2_to_sm_bytes_per_launch"] = sum(c["l1tex__m_xbar2l1tex_read_bytes.sum"] for c in h) / len(h)
     with open(os.path.join(out_dir, f"{tag}_layer_kernel_ncu.md"), "w") as f:
         f.write(f"# ncu --set full, layer_tc_kernel ({tag})\n\n`ncu --set full --clock-control none --import-source on -k regex:layer_tc` "
                 "on 262,144 poses.  One row per captured launch.\n\n")
