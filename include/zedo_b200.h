@@ -88,14 +88,21 @@ int zedo_plan_reserve(zedo_plan* plan, int32_t max_steps, int32_t gemm_mode, voi
 /* ---- process-wide tuning options ---------------------------------------------------------------
  * Defaults are the product path; none selects a non-CUDA path.  Initial values may be given through the
  * environment variable named beside each option (read once, at first use). */
-#define ZEDO_OPT_GEOM_KERNEL     0  /* geometry kernel: 0 = by batch size, 1 = warp per pose, 2 = 128-pose CTAs (ZEDO_GEOM) */
+#define ZEDO_OPT_GEOM_KERNEL     0  /* geometry kernel: 0 = by batch size, 1 = warp per pose, 2 = 128-pose CTAs, 3 = (zedo_oil_loop) rays precomputed once per loop (ZEDO_GEOM) */
 #define ZEDO_OPT_PDL             1  /* programmatic dependent launch between the kernels of a step (ZEDO_PDL), default 1 */
 #define ZEDO_OPT_SMALL_TILES     2  /* batches of at most this many 128-row tiles use 64-channel tiles (ZEDO_SMALL_TILES), 18;
                                        read by zedo_plan_create */
 #define ZEDO_OPT_CTA_PAIRS       3  /* cta_group::2 kernel for the 1024x1024 layers (ZEDO_TC2), default 1; read by plan_create */
 #define ZEDO_OPT_FP8LO_FORCE     4  /* e4m3 low-order products even for heavy-tailed weights (ZEDO_FP8LO_FORCE), default 0 */
 #define ZEDO_OPT_EXPERIMENT      5  /* timing experiments; only in builds with -DZEDO_EXPERIMENTS=1 (ZEDO_DBG) */
-#define ZEDO_OPT_COUNT           6
+#define ZEDO_OPT_LEAN_EW         6  /* epilogue warps of the K = 64 first layer (no residual / addend operands): 16 (default)
+                                      or 8 (ZEDO_LEAN_EW) */
+#define ZEDO_OPT_GRAPH           7  /* zedo_oil_loop as ONE cudaGraphLaunch: the call is captured the first time it is seen and
+                                      replayed while it repeats verbatim (same buffers, sizes, schedule); default 0 --
+                                      capturing ~7 launches per step costs about a third of a small-batch loop, so it pays
+                                      for callers that replay a loop on persistent buffers; calls on the legacy default
+                                      stream (which cannot be captured) are launched directly (ZEDO_GRAPH) */
+#define ZEDO_OPT_COUNT           8
 int zedo_set_option(int32_t option, int32_t value);
 int zedo_get_option(int32_t option, int32_t* value);
 

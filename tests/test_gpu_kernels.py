@@ -94,27 +94,35 @@ def test_grad_field_vs_oracle_random(zr, geom_kernel, J, B):
     assert np.array_equal(T_back.cpu().numpy(), T_in)
 
 
-@pytest.mark.parametrize("J,B", [(17, 1000), (12, 333), (17, 129)])
+@pytest.mark.parametrize("J,B", [(17, 1000), (12, 333), (17, 129), (21, 71)])
 def test_geometry_kernels_agree_bitwise(zr, monkeypatch, J, B):
-    """Same poses through both kernels (ragged last CTA): bit-identical -- they share the per-joint arithmetic
-    and the summation order -- incl. the operand image emitted for the first layer (same loop result)."""
+    """Same poses through the warp kernel, the 128-pose-CTA kernel and (inside zedo_oil_loop) the per-step kernel on rays
+    precomputed once per loop (ragged last CTA, confidences that need the in-place clamp): bit-identical -- they share
+    the per-joint arithmetic and the summation order -- incl. the operand image emitted for the first layer (same
+    loop result), the dumped intermediate states and the clamped confidences left behind."""
     ds = zo.make_synthetic_dataset(B, n_joints=J, seed=3)
     x0 = (ds["db_3d"] + np.random.default_rng(2).normal(0, 0.05, ds["db_3d"].shape)).astype(np.float32)
-    uv, K, conf = ds["db_2d"][:, :, :2], ds["camera_param"], ds["db_2d"][:, :, 2]
+    uv, K, conf = ds["db_2d"][:, :, :2], ds["camera_param"], ds["db_2d"][:, :, 2].copy()
+    conf[::7, 0] = 1.5
+    conf[::5, 1] = 0.0
     W = zo.make_weights(seed=0, n_joints=J)
     plan = zr.ScorePlan(W, n_joints=J, max_batch=B)
     out = {}
-    for poses in ("warp", "block"):
-        zr._native.set_option(zr._native.OPT_GEOM_KERNEL, {"warp": 1, "block": 2}[poses])
+    for poses in ("warp", "block", "rays"):
+        zr._native.set_option(zr._native.OPT_GEOM_KERNEL, {"warp": 1, "block": 2, "rays": 3}[poses])
         g, T = zr.grad_field(dev(uv), dev(x0), dev(K), conf=dev(conf))
-        x, Tl = dev(x0), dev(zo.init_translation(uv, K, 3.0).reshape(B, 3))
-        dump = plan.oil_loop(x, Tl, dev(uv), dev(K), dev(conf), zo.oil_time_grid()[500:504], phase_switch=2,
-                             dump_steps=range(4), mode="split3")
-        out[poses] = (g, T, x, Tl, dump)
+        x, Tl, cl = dev(x0), dev(zo.init_translation(uv, K, 3.0).reshape(B, 3)), dev(conf)
+        dump = plan.oil_loop(x, Tl, dev(uv), dev(K), cl, zo.oil_time_grid()[500:506], phase_switch=2,
+                             dump_steps=range(6), mode="split3")
+        x2, T2 = dev(x0), dev(zo.init_translation(uv, K, 3.0).reshape(B, 3))
+        plan.oil_loop(x2, T2, dev(uv), dev(K), None, zo.oil_time_grid()[500:503], phase_switch=1, mode="split3")
+        out[poses] = (g, T, x, Tl, dump, cl, x2, T2)
     plan.close()
     zr._native.set_option(zr._native.OPT_GEOM_KERNEL, 0)
-    for a, b in zip(out["warp"], out["block"]):
-        assert torch.equal(a, b)
+    assert float(out["warp"][5].max()) == 1.0 and float(out["warp"][5].min()) == pytest.approx(1e-4)
+    for other in ("block", "rays"):
+        for a, b in zip(out["warp"], out[other]):
+            assert torch.equal(a, b)
 
 
 def test_grad_field_empty_batch(zr, geom_kernel):
@@ -673,6 +681,58 @@ def test_oil_loop_on_a_side_stream_with_table_growth(zr):
     for x, T in results[1:]:
         assert torch.equal(x, results[0][0]) and torch.equal(T, results[0][1])
     assert bool(torch.isfinite(results[0][0]).all())
+
+
+def test_oil_loop_as_one_cuda_graph(zr):
+    """ZEDO_OPT_GRAPH: the loop call is captured once and replayed (one cudaGraphLaunch per loop) while it repeats
+    verbatim; results, dumps and the kernel count are those of the directly launched loop; a changed argument
+    re-captures; a call on the legacy default stream is launched directly."""
+    nat = zr._native
+    B = 300
+    ds = zo.make_synthetic_dataset(B, seed=5)
+    plan = zr.ScorePlan(zo.make_weights(seed=0), n_joints=17, max_batch=B, device=0)
+    uv, K, conf0 = dev(ds["db_2d"][:, :, :2]), dev(ds["camera_param"]), dev(ds["db_2d"][:, :, 2])
+    x0 = dev(ds["db_3d"] + 0.05)
+    T0 = dev(zo.init_translation(ds["db_2d"][:, :, :2], ds["camera_param"], 3.0).reshape(B, 3))
+    ts = zo.oil_time_grid()[:60]
+    x, T, conf = x0.clone(), T0.clone(), conf0.clone()
+    kw = dict(phase_switch=12, dump_steps=(3, 59))
+
+    def reset():
+        x.copy_(x0), T.copy_(T0), conf.copy_(conf0)
+
+    s = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    try:
+        with torch.cuda.stream(s):
+            n0 = nat.launch_count()
+            ref_dump = plan.oil_loop(x, T, uv, K, conf, ts, **kw)
+            s.synchronize()
+            direct = nat.launch_count() - n0
+            ref = (x.clone(), T.clone(), ref_dump.clone())
+            nat.set_option(nat.OPT_GRAPH, 1)
+            dump = torch.empty_like(ref_dump)
+            for rep in range(3):  # capture + launch, then two replays of the cached graph
+                reset()
+                n0 = nat.launch_count()
+                d = plan.oil_loop(x, T, uv, K, conf, ts, dump_out=dump, **kw)
+                s.synchronize()
+                assert nat.launch_count() - n0 == direct
+                assert torch.equal(x, ref[0]) and torch.equal(T, ref[1]) and torch.equal(d, ref[2])
+            # a different phase switch is a different loop: re-captured, not replayed (T is never re-solved here)
+            reset()
+            plan.oil_loop(x, T, uv, K, conf, ts, phase_switch=60)
+            s.synchronize()
+            assert torch.equal(T, T0) and not torch.equal(x, ref[0])
+        # legacy default stream: cannot be captured, launched directly, same result
+        torch.cuda.synchronize()
+        reset()
+        d = plan.oil_loop(x, T, uv, K, conf, ts, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(x, ref[0]) and torch.equal(T, ref[1]) and torch.equal(d, ref[2])
+    finally:
+        nat.set_option(nat.OPT_GRAPH, 0)
+        plan.close()
 
 
 def test_duplicate_dump_steps_are_served(zr, plan17, golden):

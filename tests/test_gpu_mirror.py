@@ -61,6 +61,25 @@ def test_model_forward_matches_reference(lib, model, golden):
     assert rel_err(out2, g["out_0.1"] + 1.0) < 2e-5
     with torch.no_grad():
         model.post_dense.bias.sub_(1.0)
+    # the mirror's EMA writes through the parameters (version counters move): copy_to / restore re-pack the plan
+    from lib.algorithms.ema import ExponentialMovingAverage
+    ema = ExponentialMovingAverage(model.parameters(), decay=0.999)
+    with torch.no_grad():
+        ema.shadow_params[-1].add_(2.0)  # post_dense.bias is the last parameter
+    ema.store(model.parameters())
+    ema.copy_to(model.parameters())
+    out3 = model(x, torch.ones(8, device="cuda") * 99.9, None, None).cpu().numpy()
+    assert rel_err(out3, g["out_0.1"] + 2.0) < 2e-5
+    ema.restore(model.parameters())
+    out4 = model(x, torch.ones(8, device="cuda") * 99.9, None, None).cpu().numpy()
+    assert rel_err(out4, g["out_0.1"]) < 2e-5
+    # a write through .data is invisible to the cache key: invalidate_plan() is the documented hook
+    model.post_dense.bias.data.add_(1.0)
+    model.invalidate_plan()
+    out5 = model(x, torch.ones(8, device="cuda") * 99.9, None, None).cpu().numpy()
+    assert rel_err(out5, g["out_0.1"] + 1.0) < 2e-5
+    model.post_dense.bias.data.sub_(1.0)
+    model.invalidate_plan()
 
 
 def test_driver_loop_through_the_mirror(lib, model, golden):

@@ -124,6 +124,14 @@ def test_mirror_model_state_dict_contract(zr):
     ema.load_state_dict(ckpt["ema"])
     assert np.array_equal(m.b2_dense1.weight.detach().numpy(), W["b2_dense1.weight"])
     assert sum(p.numel() for p in m.parameters()) == 7_203_379
+    # copy_to / restore write through the parameters: their version counters (the plan cache key) move
+    v0 = m.post_dense.bias._version
+    ema.store(m.parameters())
+    ema.copy_to(m.parameters())
+    v1 = m.post_dense.bias._version
+    ema.restore(m.parameters())
+    assert v0 < v1 < m.post_dense.bias._version
+    assert np.array_equal(m.b2_dense1.weight.detach().numpy(), W["b2_dense1.weight"])
     with pytest.raises(RuntimeError):  # model on CPU: no CPU path
         m.eval()
         m(torch.zeros(2, 17, 3), torch.ones(2), None, None)

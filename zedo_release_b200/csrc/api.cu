@@ -23,9 +23,9 @@ struct Options {
   std::atomic<int> v[ZEDO_OPT_COUNT];
   Options() {
     const int defaults[ZEDO_OPT_COUNT] = {/*GEOM_KERNEL*/ 0, /*PDL*/ 1, /*SMALL_TILES*/ 18, /*CTA_PAIRS*/ 1,
-                                          /*FP8LO_FORCE*/ 0, /*EXPERIMENT*/ 0};
+                                          /*FP8LO_FORCE*/ 0, /*EXPERIMENT*/ 0, /*LEAN_EW*/ 16, /*GRAPH*/ 0};
     const char* env[ZEDO_OPT_COUNT] = {"ZEDO_GEOM", "ZEDO_PDL", "ZEDO_SMALL_TILES", "ZEDO_TC2", "ZEDO_FP8LO_FORCE",
-                                       "ZEDO_DBG"};
+                                       "ZEDO_DBG", "ZEDO_LEAN_EW", "ZEDO_GRAPH"};
     for (int i = 0; i < ZEDO_OPT_COUNT; ++i) {
       int val = defaults[i];
       if (const char* e = getenv(env[i])) {  // read once, here; never on a launch path
@@ -212,6 +212,9 @@ struct zedo_plan {
   std::vector<float*> act32;       // validation mode, lazily allocated [m_pad, H]
   float* x32 = nullptr;            // [m_pad, D] scratch pose buffer
   float* row_norms = nullptr;      // [m_pad, 2] per-row |score|, |z| of the Langevin corrector
+  float4* rays_a = nullptr;        // OIL loop: per joint slot (unit ray, conf^2), geom.cu "precomputed rays"
+  float2* rays_b = nullptr;        // ... (ray_x, ray_y)
+  double* pose_c = nullptr;        // ... per pose (1/S, den, Sxz, Syz)
   int64_t eps_rows = -1;           // rows of the network output currently held in `eps` (-1: none)
   // bias tables
   int table_steps = 0;
@@ -229,6 +232,12 @@ struct zedo_plan {
   std::vector<float*> static_rows;             // per table row: NULL or a [H] vector broadcast over the steps
   float* zeros_h = nullptr;
   std::vector<void*> owned;
+  // ZEDO_OPT_GRAPH: the last zedo_oil_loop call captured as one CUDA graph, replayed while the call repeats verbatim
+  struct LoopGraph {
+    cudaGraphExec_t exec = nullptr;
+    std::vector<unsigned char> key;  // every argument and option the captured launches depend on
+    int64_t kernels = 0;             // kernel launches inside the graph
+  } loop_graph;
   // live kernel timing (zedo_plan_profile)
   bool prof_on = false;
   int prof_stride = 1;
@@ -869,6 +878,9 @@ static int plan_create_impl(zedo_plan** out, const zedo_net_desc* desc, int32_t 
   PLAN_TRY(dev_alloc(p, &p->eps, (size_t)p->m_pad * 64));
   PLAN_TRY(dev_alloc(p, &p->x32, (size_t)p->m_pad * D));
   PLAN_TRY(dev_alloc(p, &p->row_norms, (size_t)p->m_pad * 2));
+  PLAN_TRY(dev_alloc(p, &p->rays_a, oil_rays_slots(p->m_pad, desc->n_joints)));
+  PLAN_TRY(dev_alloc(p, &p->rays_b, oil_rays_slots(p->m_pad, desc->n_joints)));
+  PLAN_TRY(dev_alloc(p, &p->pose_c, (size_t)p->m_pad * 4));
   PLAN_TRY(ensure_tables(p, 1, (cudaStream_t)0));
   PLAN_TRY((int)cudaDeviceSynchronize());
 #undef NEED
@@ -961,6 +973,7 @@ int zedo_plan_destroy(zedo_plan* plan) {
   DeviceGuard on_device(plan->device);
   cudaDeviceSynchronize();
   zedo_plan_profile(plan, 0, 1);
+  if (plan->loop_graph.exec != nullptr) cudaGraphExecDestroy(plan->loop_graph.exec);
   for (void* q : plan->owned) cudaFree(q);
   delete plan;
   return 0;
@@ -1035,26 +1048,18 @@ int zedo_sde_step(zedo_plan* plan, const float* x, float t, const float* z, int3
   return launch_sde_update(x, plan->eps, 64, z, c, predictor, probability_flow, x_next, x_mean, B, plan->D, st);
 }
 
-static int oil_loop_impl(zedo_plan* plan, float* x, float* T, const float* uv, const float* K, float* conf,
-                         const float* t_sched, int32_t steps, int32_t phase_switch, float beta_min, float beta_max,
-                         int32_t n_scales, float* dump, const int32_t* dump_steps, int32_t n_dump, int64_t B,
-                         int32_t gemm_mode, void* stream) {
-  int rc = check_batch(plan, B);
-  if (rc) return rc;
-  if (!x || !T || !uv || !K || !t_sched || steps < 0 || steps > (1 << 20) || n_scales < 1) return ZEDO_E_INVALID;
-  if (n_dump > 0 && (!dump || !dump_steps)) return ZEDO_E_INVALID;
-  for (int k = 0; k < n_dump; ++k)
-    if (dump_steps[k] < 0 || dump_steps[k] >= steps || (k > 0 && dump_steps[k] <= dump_steps[k - 1]))
-      return ZEDO_E_INVALID;  // strictly ascending, inside the schedule
-  if (B == 0 || steps == 0) return 0;
-  cudaStream_t st = (cudaStream_t)stream;
-  plan->eps_rows = -1;
+// the launches of one loop call (tables already built): rays, steps x {geometry -> network}, last predictor update
+static int oil_loop_enqueue(zedo_plan* plan, float* x, float* T, const float* uv, const float* K, float* conf,
+                            const float* t_sched, int32_t steps, int32_t phase_switch, float beta_min, float beta_max,
+                            int32_t n_scales, float* dump, const int32_t* dump_steps, int32_t n_dump, int64_t B,
+                            int32_t gemm_mode, cudaStream_t st) {
+  int rc;
   const int J = plan->desc.n_joints, D = plan->D;
-  std::vector<float> t999((size_t)steps);
-  for (int i = 0; i < steps; ++i) t999[i] = t_sched[i] * 999.0f;
-  if ((rc = build_tables(plan, t999.data(), steps, st))) return rc;
-  // the pageable t999 buffer has been consumed by the (staged) async copy once the call returns
   const bool tc = gemm_mode != ZEDO_GEMM_FP32;
+  // uv, K and the clamped conf are loop invariants: with a batch that fills the GPU the rays, weights and the
+  // pose-independent half of the normal equations are evaluated once here (bit-identical to the per-step evaluation)
+  const bool rays = plan->rays_a != nullptr && oil_rays_selected(B);
+  if (rays && (rc = launch_oil_rays(uv, K, conf, plan->rays_a, plan->rays_b, plan->pose_c, B, J, st))) return rc;
   // Step i = geometry(i) -> network(i) -> predictor update(i).  The update of step i is fused into the geometry
   // kernel of step i+1 (same float32 ops; x makes one HBM round trip per step instead of two); the last step's
   // update runs as its own kernel.  A requested dump of step i is written by whichever kernel applies update i.
@@ -1070,8 +1075,12 @@ static int oil_loop_impl(zedo_plan* plan, float* x, float* T, const float* uv, c
       // gradient_field_gen + `denoise_x += joint_gradient` (opt_main.py:203-208); conf is clamped in place by
       // the first call of the reference and stays clamped
       ProfScope ps(plan, 3, st);
-      rc = launch_grad_field(uv, x, K, conf, T, i >= phase_switch ? 1 : 0, i == 0 ? 1 : 0, nullptr, x,
+      if (rays)
+        rc = launch_oil_geom(plan->rays_a, plan->rays_b, plan->pose_c, x, T, i >= phase_switch ? 1 : 0,
                              tc ? plan->xa : nullptr, B, J, st, i > 0 ? plan->eps : nullptr, &prev, dump_ptr);
+      else
+        rc = launch_grad_field(uv, x, K, conf, T, i >= phase_switch ? 1 : 0, i == 0 ? 1 : 0, nullptr, x,
+                               tc ? plan->xa : nullptr, B, J, st, i > 0 ? plan->eps : nullptr, &prev, dump_ptr);
     }
     if (rc) return rc;
     const float* tbl = plan->table + (size_t)i * plan->L * plan->H;
@@ -1089,6 +1098,83 @@ static int oil_loop_impl(zedo_plan* plan, float* x, float* T, const float* uv, c
                                   cudaMemcpyDeviceToDevice, st));
   return 0;
 }
+
+static void drop_loop_graph(zedo_plan* plan) {
+  if (plan->loop_graph.exec != nullptr) cudaGraphExecDestroy(plan->loop_graph.exec);
+  plan->loop_graph = zedo_plan::LoopGraph{};
+}
+
+static void key_bytes(std::vector<unsigned char>& k, const void* v, size_t n) {
+  const unsigned char* b = static_cast<const unsigned char*>(v);
+  k.insert(k.end(), b, b + n);
+}
+#define key_put(k, v) key_bytes(k, &(v), sizeof(v))
+
+static int oil_loop_impl(zedo_plan* plan, float* x, float* T, const float* uv, const float* K, float* conf,
+                         const float* t_sched, int32_t steps, int32_t phase_switch, float beta_min, float beta_max,
+                         int32_t n_scales, float* dump, const int32_t* dump_steps, int32_t n_dump, int64_t B,
+                         int32_t gemm_mode, void* stream) {
+  int rc = check_batch(plan, B);
+  if (rc) return rc;
+  if (!x || !T || !uv || !K || !t_sched || steps < 0 || steps > (1 << 20) || n_scales < 1) return ZEDO_E_INVALID;
+  if (n_dump > 0 && (!dump || !dump_steps)) return ZEDO_E_INVALID;
+  for (int k = 0; k < n_dump; ++k)
+    if (dump_steps[k] < 0 || dump_steps[k] >= steps || (k > 0 && dump_steps[k] <= dump_steps[k - 1]))
+      return ZEDO_E_INVALID;  // strictly ascending, inside the schedule
+  if (B == 0 || steps == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  plan->eps_rows = -1;
+  std::vector<float> t999((size_t)steps);
+  for (int i = 0; i < steps; ++i) t999[i] = t_sched[i] * 999.0f;
+  if ((rc = build_tables(plan, t999.data(), steps, st))) return rc;
+  // the pageable t999 buffer has been consumed by the (staged) async copy once the call returns
+  if (gemm_mode == ZEDO_GEMM_FP32 && (rc = ensure_act32(plan, st))) return rc;  // never allocate inside a capture
+  // (the legacy default stream cannot be captured: such calls are launched directly)
+  if (!option_get(ZEDO_OPT_GRAPH) || plan->prof_on || st == nullptr || st == cudaStreamLegacy)
+    return oil_loop_enqueue(plan, x, T, uv, K, conf, t_sched, steps, phase_switch, beta_min, beta_max, n_scales, dump,
+                            dump_steps, n_dump, B, gemm_mode, st);
+
+  // ---- ZEDO_OPT_GRAPH: one cudaGraphLaunch per loop.  The whole call is captured the first time it is seen and
+  // replayed for as long as it repeats verbatim (same buffers, sizes, schedule, options); anything else re-captures.
+  std::vector<unsigned char> key;
+  key_put(key, x); key_put(key, T); key_put(key, uv); key_put(key, K); key_put(key, conf); key_put(key, dump);
+  key_put(key, B); key_put(key, steps); key_put(key, phase_switch); key_put(key, beta_min); key_put(key, beta_max);
+  key_put(key, n_scales); key_put(key, gemm_mode); key_put(key, n_dump); key_put(key, plan->table);
+  for (int i = 0; i < steps; ++i) key_put(key, t_sched[i]);
+  for (int k = 0; k < n_dump; ++k) key_put(key, dump_steps[k]);
+  for (int o = 0; o < ZEDO_OPT_COUNT; ++o) {
+    const int ov = option_get(o);
+    key_put(key, ov);
+  }
+  if (plan->loop_graph.exec == nullptr || plan->loop_graph.key != key) {
+    drop_loop_graph(plan);
+    const int64_t before = g_launches.load();
+    ZEDO_CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    rc = oil_loop_enqueue(plan, x, T, uv, K, conf, t_sched, steps, phase_switch, beta_min, beta_max, n_scales, dump,
+                          dump_steps, n_dump, B, gemm_mode, st);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(st, &graph);  // always: leaves the stream usable after an error
+    const int64_t kernels = g_launches.load() - before;
+    g_launches.fetch_sub(kernels);                           // captured, not launched yet
+    if (rc == 0 && e != cudaSuccess) rc = (int)e;
+    if (rc == 0) {
+      const cudaError_t ei = cudaGraphInstantiate(&plan->loop_graph.exec, graph, 0);
+      if (ei != cudaSuccess) rc = (int)ei;
+    }
+    if (graph != nullptr) cudaGraphDestroy(graph);
+    if (rc) {
+      cudaGetLastError();
+      plan->loop_graph.exec = nullptr;
+      return rc;
+    }
+    plan->loop_graph.key = key;
+    plan->loop_graph.kernels = kernels;
+  }
+  ZEDO_CUDA_TRY(cudaGraphLaunch(plan->loop_graph.exec, st));
+  count_launch((int)plan->loop_graph.kernels);
+  return 0;
+}
+#undef key_put
 
 int zedo_oil_loop(zedo_plan* plan, float* x, float* T, const float* uv, const float* K, float* conf,
                   const float* t_sched, int32_t steps, int32_t phase_switch, float beta_min, float beta_max,

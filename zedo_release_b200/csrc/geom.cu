@@ -109,12 +109,18 @@ __device__ __forceinline__ void solve_translation(const NormalEq& e, float& T0, 
   }
 }
 
-// unit ray, p = X + T, g = (p . r^) r^ - p  (:33-36,99,109); returns g, and X + g in n
-__device__ __forceinline__ void project_on_ray(const Ray& r, float X0, float X1, float X2, float T0, float T1,
-                                               float T2, float* g, float* n) {
+// unit ray r^ = r / |r|  (:33-36)
+__device__ __forceinline__ void unit_ray(const Ray& r, float& hx, float& hy, float& hz) {
   const float nrm =
       __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(r.x, r.x), __fmul_rn(r.y, r.y)), __fmul_rn(r.z, r.z)));
-  const float hx = __fdiv_rn(r.x, nrm), hy = __fdiv_rn(r.y, nrm), hz = __fdiv_rn(r.z, nrm);
+  hx = __fdiv_rn(r.x, nrm);
+  hy = __fdiv_rn(r.y, nrm);
+  hz = __fdiv_rn(r.z, nrm);
+}
+
+// p = X + T, g = (p . r^) r^ - p  (:99,109); returns g, and X + g in n
+__device__ __forceinline__ void project_on_unit_ray(float hx, float hy, float hz, float X0, float X1, float X2,
+                                                    float T0, float T1, float T2, float* g, float* n) {
   const float p0 = __fadd_rn(X0, T0), p1 = __fadd_rn(X1, T1), p2 = __fadd_rn(X2, T2);
   const float d = __fadd_rn(__fadd_rn(__fmul_rn(p0, hx), __fmul_rn(p1, hy)), __fmul_rn(p2, hz));
   g[0] = __fsub_rn(__fmul_rn(d, hx), p0);
@@ -123,6 +129,13 @@ __device__ __forceinline__ void project_on_ray(const Ray& r, float X0, float X1,
   n[0] = __fadd_rn(X0, g[0]);
   n[1] = __fadd_rn(X1, g[1]);
   n[2] = __fadd_rn(X2, g[2]);
+}
+
+__device__ __forceinline__ void project_on_ray(const Ray& r, float X0, float X1, float X2, float T0, float T1,
+                                               float T2, float* g, float* n) {
+  float hx, hy, hz;
+  unit_ray(r, hx, hy, hz);
+  project_on_unit_ray(hx, hy, hz, X0, X1, X2, T0, T1, T2, g, n);
 }
 
 __device__ __forceinline__ float clamp_conf(float c) {
@@ -432,6 +445,233 @@ grad_field_block_kernel(const float* __restrict__ uv, const float* x, const floa
   }
 }
 
+// ---- the OIL loop's geometry step on precomputed rays ----------------------------------------------------------
+// uv, K and (after the first call's in-place clamp) conf do not change during zedo_oil_loop, so everything of
+// gradient_field_gen that depends on them alone is evaluated ONCE per loop by oil_rays_kernel -- with the very functions
+// above, in the summation order of the kernels above, hence bit-identical -- and the per-step kernel is left with the
+// part that depends on the pose: b = A^T (w b_rows) of the normal equations, the back-substitution and the projection.
+// Per step and pose that removes 7 IEEE divisions and a square root per joint, the K inverse and four of the seven
+// float64 reductions (~3x fewer instructions); the price is 24 B per joint slot of ray data instead of 8 B of (u, v).
+//
+// Layout (one entry per lane of the step kernel's per-pose phase, so a warp's loads are 512 / 256 contiguous bytes):
+//   slot(pose, it, q) = ((pose / 8) * n_it + it) * 32 + (pose % 8) * 4 + q      joint j = q + 4 it, n_it = ceil(J / 4)
+//   rays_a[slot] = (r^_x, r^_y, r^_z, w = conf^2)      rays_b[slot] = (r_x, r_y)      zeros for j >= J
+//   pose_c[pose] = (1/S, den, Sxz, Syz)  float64: the pose-independent part of solve_translation
+constexpr int kRayPoses = 64;                  // poses per CTA of the step kernel
+constexpr int kRayThreads = kRayPoses * kGeomTpp;
+
+__host__ __device__ inline int ray_iters(int J) { return (J + kGeomTpp - 1) / kGeomTpp; }
+
+__global__ void __launch_bounds__(kRayThreads)
+oil_rays_kernel(const float* __restrict__ uv, const float* __restrict__ Kmat, float* conf, float4* __restrict__ rays_a,
+                float2* __restrict__ rays_b, double* __restrict__ pose_c, int64_t B, int J) {
+  const int64_t p0 = (int64_t)blockIdx.x * kRayPoses;
+  const int tid = threadIdx.x, pl = tid >> 2, q = tid & 3;
+  const int64_t pose = p0 + pl;  // B_pad8 rows are covered by the grid; rows >= B get zero entries
+  const int n_it = ray_iters(J);
+  const bool live = pose < B;
+  const int64_t pp = live ? pose : B - 1;  // idle quads recompute the last pose (converged shuffles), results dropped
+  float Km[9], Ki[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Km[i] = Kmat[pp * 9 + i];
+  inv3x3_rn(Km, Ki);
+  NormalEq e{0, 0, 0, 0, 0, 0, 0};
+  const int64_t slot0 = ((pose >> 3) * n_it) * 32 + (pose & 7) * 4 + q;
+  for (int it = 0; it < n_it; ++it) {
+    const int j = q + kGeomTpp * it;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 b = make_float2(0.f, 0.f);
+    if (j < J) {
+      const float2 p2 = *reinterpret_cast<const float2*>(uv + (pp * J + j) * 2);
+      float c = 1.f;
+      if (conf != nullptr) {
+        c = clamp_conf(conf[pp * J + j]);
+        if (live) conf[pp * J + j] = c;  // the reference clamps in place at its first call (:65-66)
+      }
+      const Ray r = back_project(Ki, p2.x, p2.y);
+      const float w = __fmul_rn(c, c);
+      unit_ray(r, a.x, a.y, a.z);
+      a.w = w;
+      b = make_float2(r.x, r.y);
+      // the X-independent sums of joint_normal_eq, same products, same order
+      const float ax = __fmul_rn(r.x, w), ay = __fmul_rn(r.y, w), am = -w;
+      e.S = __dadd_rn(e.S, (double)__fmul_rn(am, am));
+      e.Sxz = __dadd_rn(e.Sxz, (double)__fmul_rn(am, ax));
+      e.Syz = __dadd_rn(e.Syz, (double)__fmul_rn(am, ay));
+      e.Szz = __dadd_rn(e.Szz, __dadd_rn((double)__fmul_rn(ax, ax), (double)__fmul_rn(ay, ay)));
+    }
+    if (live) {
+      rays_a[slot0 + (int64_t)it * 32] = a;
+      rays_b[slot0 + (int64_t)it * 32] = b;
+    } else {
+      rays_a[slot0 + (int64_t)it * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rays_b[slot0 + (int64_t)it * 32] = make_float2(0.f, 0.f);
+    }
+  }
+  e.S = quad_sum_f64(e.S);
+  e.Sxz = quad_sum_f64(e.Sxz);
+  e.Syz = quad_sum_f64(e.Syz);
+  e.Szz = quad_sum_f64(e.Szz);
+  if (live && q == 0) {
+    const double iS = __ddiv_rn(1.0, e.S);
+    const double den = __dsub_rn(e.Szz, __dmul_rn(__dadd_rn(__dmul_rn(e.Sxz, e.Sxz), __dmul_rn(e.Syz, e.Syz)), iS));
+    double* pc = pose_c + pose * 4;
+    pc[0] = iS;
+    pc[1] = den;
+    pc[2] = e.Sxz;
+    pc[3] = e.Syz;
+  }
+}
+
+// One OIL step's geometry for kRayPoses poses per CTA: fused predictor update of the previous step (as in the kernels
+// above), then -- four threads per pose, thread q owns joints q, q + 4, ... -- the translation solve (SOLVE) and the
+// projection on the precomputed unit rays; x is updated in place and the first GEMM's operand emitted.
+template <bool SOLVE, int NIT>
+__global__ void __launch_bounds__(kRayThreads)
+oil_geom_kernel(const float4* __restrict__ rays_a, const float2* __restrict__ rays_b,
+                const double* __restrict__ pose_c, float* x, float* T, __half* __restrict__ xa, int64_t B, int J,
+                const float* __restrict__ eps_prev, float neg_half_beta, float gsq, float std, float dt,
+                float* __restrict__ dump) {
+  extern __shared__ __align__(16) float geom_smem[];
+  const int D = 3 * J, Dp = D | 1;
+  float* xs = geom_smem;               // [P][Dp]
+  float* ts = xs + kRayPoses * Dp;     // [P][3]
+  const int64_t p0 = (int64_t)blockIdx.x * kRayPoses;
+  const int n = (int)((B - p0) < kRayPoses ? (B - p0) : kRayPoses);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int kWarps = kRayThreads / 32;
+  const int n_it = NIT ? NIT : ray_iters(J);
+
+  griddep_wait();  // PDL: x / eps / T come from the previous kernels
+  // stage the poses, one row per warp iteration (coalesced), applying the previous step's predictor update
+#pragma unroll 2
+  for (int r = warp; r < n; r += kWarps) {
+    const float* xg = x + (p0 + r) * D;
+    const float* eg = eps_prev != nullptr ? eps_prev + (p0 + r) * 64 : nullptr;
+    for (int c = lane; c < D; c += 32) {
+      float xv = xg[c];
+      if (eg != nullptr) {
+        xv = em_pf_update(xv, eg[c], neg_half_beta, gsq, std, dt);
+        if (dump != nullptr) dump[(p0 + r) * D + c] = xv;
+      }
+      xs[r * Dp + c] = xv;
+    }
+  }
+  if (!SOLVE)
+    for (int i = tid; i < n * 3; i += kRayThreads) ts[i] = T[p0 * 3 + i];
+  __syncthreads();
+
+  if (((tid & ~31) >> 2) < n) {
+    const int pl = tid >> 2, q = tid & 3;
+    const bool live = pl < n;
+    const int pp = live ? pl : n - 1;
+    const int64_t slot0 = (((p0 + pp) >> 3) * n_it) * 32 + (pp & 7) * 4 + q;
+    const float4* ra = rays_a + slot0;
+    float* xp = xs + pp * Dp;
+    constexpr int kMaxIt = NIT ? NIT : 8;  // J <= 32
+    float4 hw[kMaxIt];
+#pragma unroll
+    for (int it = 0; it < kMaxIt; ++it)
+      hw[it] = it < n_it ? ra[it * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float T0, T1, T2;
+    if (SOLVE) {
+      const float2* rb = rays_b + slot0;
+      float2 rxy[kMaxIt];
+#pragma unroll
+      for (int it = 0; it < kMaxIt; ++it) rxy[it] = it < n_it ? rb[it * 32] : make_float2(0.f, 0.f);
+      const double* pc = pose_c + (p0 + pp) * 4;
+      const double iS = pc[0], den = pc[1], Sxz = pc[2], Syz = pc[3];
+      double b0 = 0.0, b1 = 0.0, b2 = 0.0;
+#pragma unroll
+      for (int it = 0; it < kMaxIt; ++it) {
+        const int j = q + kGeomTpp * it;
+        if (it < n_it && j < J) {
+          // the X-dependent part of joint_normal_eq, same products, same order
+          const float X0 = xp[3 * j], X1 = xp[3 * j + 1], X2 = xp[3 * j + 2];
+          const float w = hw[it].w, rx = rxy[it].x, ry = rxy[it].y;
+          const float bx = __fmul_rn(__fsub_rn(X0, __fmul_rn(X2, rx)), w);
+          const float by = __fmul_rn(__fsub_rn(X1, __fmul_rn(X2, ry)), w);
+          const float ax = __fmul_rn(rx, w), ay = __fmul_rn(ry, w), am = -w;
+          b0 = __dadd_rn(b0, (double)__fmul_rn(am, bx));
+          b1 = __dadd_rn(b1, (double)__fmul_rn(am, by));
+          b2 = __dadd_rn(b2, __dadd_rn((double)__fmul_rn(ax, bx), (double)__fmul_rn(ay, by)));
+        }
+      }
+      b0 = quad_sum_f64(b0);
+      b1 = quad_sum_f64(b1);
+      b2 = quad_sum_f64(b2);
+      // solve_translation with the pose-independent factors precomputed
+      const double num = __dsub_rn(b2, __dmul_rn(__dadd_rn(__dmul_rn(Sxz, b0), __dmul_rn(Syz, b1)), iS));
+      const double tz = __ddiv_rn(num, den);
+      T0 = (float)__dmul_rn(__dsub_rn(b0, __dmul_rn(Sxz, tz)), iS);
+      T1 = (float)__dmul_rn(__dsub_rn(b1, __dmul_rn(Syz, tz)), iS);
+      T2 = (float)tz;
+      if (T2 < 0.f) {
+        T0 = -T0;
+        T1 = -T1;
+        T2 = -T2;
+      }
+      if (live && q == 0) {
+        ts[pl * 3 + 0] = T0;
+        ts[pl * 3 + 1] = T1;
+        ts[pl * 3 + 2] = T2;
+      }
+    } else {
+      T0 = ts[pp * 3 + 0];
+      T1 = ts[pp * 3 + 1];
+      T2 = ts[pp * 3 + 2];
+    }
+    if (live) {
+#pragma unroll
+      for (int it = 0; it < kMaxIt; ++it) {
+        const int j = q + kGeomTpp * it;
+        if (it < n_it && j < J) {
+          float g[3], nx[3];
+          project_on_unit_ray(hw[it].x, hw[it].y, hw[it].z, xp[3 * j], xp[3 * j + 1], xp[3 * j + 2], T0, T1, T2, g,
+                              nx);
+          xp[3 * j] = nx[0];
+          xp[3 * j + 1] = nx[1];
+          xp[3 * j + 2] = nx[2];
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+#pragma unroll 2
+  for (int r = warp; r < n; r += kWarps) {
+    float* og = x + (p0 + r) * D;
+    for (int c = lane; c < D; c += 32) og[c] = xs[r * Dp + c];
+  }
+  if (SOLVE)
+    for (int i = tid; i < n * 3; i += kRayThreads) T[p0 * 3 + i] = ts[i];
+  if (xa != nullptr) {
+    // rows p0 .. p0 + n of the first GEMM's A operand: 64 halves per row (3J padded with zeros), hi and lo;
+    // consecutive threads write consecutive 16-byte chunks of the blocked layout
+    for (int item = tid; item < kRayPoses * (kBlockK / 8); item += kRayThreads) {
+      const int r = item & (kRayPoses - 1), ch = item / kRayPoses;
+      if (r >= n) continue;
+      const float* xp = xs + r * Dp;
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c0 = ch * 8 + 2 * e;
+        const float a = c0 < D ? xp[c0] : 0.f;
+        const float b = c0 + 1 < D ? xp[c0 + 1] : 0.f;
+        __half h0, l0, h1, l1;
+        split_hi_lo(a, h0, l0);
+        split_hi_lo(b, h1, l1);
+        hi[e] = pack_half2(h0, h1);
+        lo[e] = pack_half2(l0, l1);
+      }
+      *reinterpret_cast<uint4*>(xa + blocked_half_offset(p0 + r, ch * 8, kBlockK, kActTileRows, 0)) =
+          make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(xa + blocked_half_offset(p0 + r, ch * 8, kBlockK, kActTileRows, 1)) =
+          make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
 // x [B, D] float32 -> blocked hi/lo A operand of the first GEMM (one k-block of 64 columns)
 __global__ void pack_x_kernel(const float* __restrict__ x, __half* __restrict__ xa, int64_t B, int D) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -506,7 +746,7 @@ int launch_grad_field(const float* uv, const float* x, const float* K, float* co
   }
   // ZEDO_OPT_GEOM_KERNEL forces one kernel (tests); default: 128-pose CTAs once the batch fills the GPU
   const int forced = option_get(ZEDO_OPT_GEOM_KERNEL);
-  if (forced == 2 || (forced == 0 && B >= kGeomBlockMinPoses)) {
+  if (forced >= 2 || (forced == 0 && B >= kGeomBlockMinPoses)) {
     const size_t smem = (size_t)geom_smem_floats(J) * sizeof(float);
     if (smem > 48 * 1024) ZEDO_CUDA_TRY(ensure_max_smem((const void*)grad_field_block_kernel, (int)smem));
     ZEDO_CUDA_TRY(launch_pdl(grad_field_block_kernel, dim3((unsigned)((B + kGeomPoses - 1) / kGeomPoses)),
@@ -517,6 +757,65 @@ int launch_grad_field(const float* uv, const float* x, const float* K, float* co
                              dim3(kGeomWarps * 32), 0, st, uv, x, K, conf, T, solve_T, clamp_inplace, g, x_out, xa, B,
                              J, eps_prev, nhb, g2, sd, dt, dump));
   }
+  ZEDO_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- OIL loop on precomputed rays ----
+bool oil_rays_selected(int64_t B) {
+  const int forced = option_get(ZEDO_OPT_GEOM_KERNEL);
+  return forced == 3 || (forced == 0 && B >= kGeomBlockMinPoses);
+}
+
+size_t oil_rays_slots(int64_t rows, int J) { return (size_t)((rows + 7) / 8) * ray_iters(J) * 32; }
+
+int launch_oil_rays(const float* uv, const float* K, float* conf, float4* rays_a, float2* rays_b, double* pose_c,
+                    int64_t B, int J, cudaStream_t st) {
+  if (B == 0) return 0;
+  ZEDO_CUDA_TRY(launch_pdl(oil_rays_kernel, dim3((unsigned)((B + kRayPoses - 1) / kRayPoses)), dim3(kRayThreads), 0,
+                           st, uv, K, conf, rays_a, rays_b, pose_c, B, J));
+  ZEDO_LAUNCH_CHECK();
+  return 0;
+}
+
+template <bool SOLVE, int NIT>
+static cudaError_t launch_oil_geom_t(const float4* rays_a, const float2* rays_b, const double* pose_c, float* x,
+                                     float* T, __half* xa, int64_t B, int J, cudaStream_t st, const float* eps_prev,
+                                     float nhb, float g2, float sd, float dt, float* dump) {
+  const size_t smem = (size_t)kRayPoses * (((3 * J) | 1) + 3) * sizeof(float);
+  return launch_pdl(oil_geom_kernel<SOLVE, NIT>, dim3((unsigned)((B + kRayPoses - 1) / kRayPoses)), dim3(kRayThreads),
+                    smem, st, rays_a, rays_b, pose_c, x, T, xa, B, J, eps_prev, nhb, g2, sd, dt, dump);
+}
+
+int launch_oil_geom(const float4* rays_a, const float2* rays_b, const double* pose_c, float* x, float* T, int solve_T,
+                    __half* xa, int64_t B, int J, cudaStream_t st, const float* eps_prev, const SdeCoef* prev,
+                    float* dump) {
+  if (B == 0) return 0;
+  if (J < 1 || J > 32) return ZEDO_E_SHAPE;
+  float nhb = 0.f, g2 = 0.f, sd = 1.f, dt = 0.f;
+  if (eps_prev != nullptr && prev != nullptr) {
+    nhb = -0.5f * prev->beta_t;
+    g2 = prev->diffusion * prev->diffusion;
+    sd = prev->std;
+    dt = prev->dt;
+  } else {
+    eps_prev = nullptr;
+  }
+  const int nit = ray_iters(J);
+  cudaError_t e;
+#define ZEDO_OIL_GEOM(S, N) \
+  e = launch_oil_geom_t<S, N>(rays_a, rays_b, pose_c, x, T, xa, B, J, st, eps_prev, nhb, g2, sd, dt, dump)
+  if (solve_T) {
+    if (nit == 5) ZEDO_OIL_GEOM(true, 5);
+    else if (nit == 3) ZEDO_OIL_GEOM(true, 3);
+    else ZEDO_OIL_GEOM(true, 0);
+  } else {
+    if (nit == 5) ZEDO_OIL_GEOM(false, 5);
+    else if (nit == 3) ZEDO_OIL_GEOM(false, 3);
+    else ZEDO_OIL_GEOM(false, 0);
+  }
+#undef ZEDO_OIL_GEOM
+  ZEDO_CUDA_TRY(e);
   ZEDO_LAUNCH_CHECK();
   return 0;
 }

@@ -37,6 +37,14 @@ int launch_layer_tc2(const LayerArgs& a, int nprod, int epi, int num_sms, cudaSt
 int launch_grad_field(const float* uv, const float* x, const float* K, float* conf, float* T, int solve_T,
                       int clamp_inplace, float* g, float* x_out, __half* xa, int64_t B, int J, cudaStream_t st,
                       const float* eps_prev = nullptr, const SdeCoef* prev = nullptr, float* dump = nullptr);
+// the OIL loop's geometry on rays precomputed once per loop (geom.cu): selected by batch size / ZEDO_OPT_GEOM_KERNEL = 3
+bool oil_rays_selected(int64_t B);
+size_t oil_rays_slots(int64_t rows, int J);  // entries of rays_a / rays_b for `rows` poses
+int launch_oil_rays(const float* uv, const float* K, float* conf, float4* rays_a, float2* rays_b, double* pose_c,
+                    int64_t B, int J, cudaStream_t st);
+int launch_oil_geom(const float4* rays_a, const float2* rays_b, const double* pose_c, float* x, float* T, int solve_T,
+                    __half* xa, int64_t B, int J, cudaStream_t st, const float* eps_prev, const SdeCoef* prev,
+                    float* dump);
 int launch_pack_x(const float* x, __half* xa, int64_t B, int D, cudaStream_t st);
 int launch_sde_update(const float* x, const float* eps, int ld_eps, const float* z, const SdeCoef& c, int predictor,
                       int probability_flow, float* x_next, float* x_mean, int64_t B, int D, cudaStream_t st);

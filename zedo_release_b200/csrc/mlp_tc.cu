@@ -39,7 +39,7 @@ struct TileCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int NPROD, int EPI, int EW>
+template <int BN, int NPROD, int EPI, int EW, bool RES = true>
 __global__ void __launch_bounds__(tc_threads(EW), 1) layer_tc_kernel(const LayerArgs args) {
   using Cfg = TileCfg<BN, NPROD>;
   constexpr int S = Cfg::kStages;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) layer_tc_kernel(const Layer
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      epilogue_tile<BN, EPI, EW>(args, tmem_base + (uint32_t)(as * BN), q, chalf, r, mt, nt);
+      epilogue_tile<BN, EPI, EW, RES>(args, tmem_base + (uint32_t)(as * BN), q, chalf, r, mt, nt);
       tc_fence_before();
       mbar_arrive(&tmem_empty[as]);
     }
@@ -206,10 +206,10 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) layer_tc_kernel(const Layer
 
 // ---- host launcher ------------------------------------------------------------------------------------
 
-template <int BN, int NPROD, int EPI, int EW>
+template <int BN, int NPROD, int EPI, int EW, bool RES = true>
 static int launch_ew(const LayerArgs& a, int num_sms, cudaStream_t st) {
   using Cfg = TileCfg<BN, NPROD>;
-  auto kern = layer_tc_kernel<BN, NPROD, EPI, EW>;
+  auto kern = layer_tc_kernel<BN, NPROD, EPI, EW, RES>;
   ZEDO_CUDA_TRY(ensure_max_smem((const void*)kern, Cfg::kSmemBytes));
   const int tiles = a.m_tiles * a.n_tiles;
   if (tiles == 0) return 0;
@@ -244,6 +244,11 @@ int launch_layer_tc(const LayerArgs& a_in, int bn, int nprod, int epi, int num_s
     if (epi == EPI_LINEAR_ACT) return launch_ew<64, 4, EPI_LINEAR_ACT, 8>(a, num_sms, st);
     return ZEDO_E_INVALID;
   }
+  // the K = 64 first layer is all epilogue: without residual / addend registers 16 epilogue warps fit (4 per scheduler)
+  // (r02, same box: 0.566 -> 0.502 ms inside the loop; the lean epilogue with 8 warps is no faster than the general one)
+  if (bn == 256 && epi == EPI_GN_SILU && nprod == 3 && a.resid == nullptr && a.addend == nullptr &&
+      option_get(ZEDO_OPT_LEAN_EW) == 16)
+    return launch_ew<256, 3, EPI_GN_SILU, 16, false>(a, num_sms, st);
   if (bn == 256 && epi == EPI_GN_SILU) return launch_nprod<256, EPI_GN_SILU>(a, nprod, num_sms, st);
   if (bn == 256 && epi == EPI_LINEAR_ACT) return launch_nprod<256, EPI_LINEAR_ACT>(a, nprod, num_sms, st);
   if (bn == 64 && epi == EPI_LINEAR_F32) return launch_nprod<64, EPI_LINEAR_F32>(a, nprod, num_sms, st);

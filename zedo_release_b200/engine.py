@@ -181,9 +181,10 @@ class ScorePlan:
     def oil_loop(self, x: torch.Tensor, T: torch.Tensor, uv: torch.Tensor, K: torch.Tensor,
                  conf: Optional[torch.Tensor], t_sched: Sequence[float], phase_switch: Optional[int] = None,
                  dump_steps: Iterable[int] = (), beta_min: float = 0.1, beta_max: float = 20.0, n_scales: int = 1000,
-                 mode=None) -> Optional[torch.Tensor]:
+                 mode=None, dump_out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
         """In place on ``x`` [B,J,3] and ``T`` [B,3] (and clamps ``conf`` in place like the
-        reference).  Returns the dump tensor [n_dump,B,J,3] or None."""
+        reference).  Returns the dump tensor [n_dump,B,J,3] or None; ``dump_out`` supplies that tensor (callers
+        that replay the loop as a CUDA graph, ``_native.OPT_GRAPH``, keep every buffer of the call persistent)."""
         for name, t in (("x", x), ("T", T), ("uv", uv), ("K", K)):
             if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
                 raise ValueError(f"{name} must be a contiguous float32 CUDA tensor (updated in place)")
@@ -197,7 +198,14 @@ class ScorePlan:
         dump_steps = sorted(set(requested))  # the C ABI takes strictly ascending steps; duplicates are served below
         dump = None
         if dump_steps:
-            dump = torch.empty((len(dump_steps),) + tuple(x.shape), dtype=torch.float32, device=x.device)
+            shape = (len(dump_steps),) + tuple(x.shape)
+            if dump_out is not None:
+                if not (dump_out.is_cuda and dump_out.dtype == torch.float32 and dump_out.is_contiguous()
+                        and tuple(dump_out.shape) == shape):
+                    raise ValueError(f"dump_out must be a contiguous float32 CUDA tensor of shape {shape}")
+                dump = dump_out
+            else:
+                dump = torch.empty(shape, dtype=torch.float32, device=x.device)
         nat.check(nat.lib.zedo_oil_loop(self._h, _ptr(x), _ptr(T), _ptr(uv), _ptr(K), _ptr(conf),
                                         ts.ctypes.data_as(C.POINTER(C.c_float)), steps, int(phase_switch),
                                         float(beta_min), float(beta_max), int(n_scales), _ptr(dump),

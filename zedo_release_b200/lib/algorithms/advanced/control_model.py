@@ -101,6 +101,10 @@ class Control_ScoreModelFC_Adv(nn.Module):
                 getattr(self, dst).weight.copy_(getattr(self, src).weight)
                 getattr(self, dst).bias.copy_(getattr(self, src).bias)
 
+    def invalidate_plan(self):
+        """See ``ScoreModelFC_Adv.invalidate_plan``."""
+        self._plans.invalidate()
+
     def zedo_plan(self, batch):
         return self._plans.get(self, batch, self.n_joints, self.hidden_dim, self.embed_dim, self.n_blocks)
 

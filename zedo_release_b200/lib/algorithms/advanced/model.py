@@ -55,9 +55,17 @@ class GaussianFourierProjection(nn.Module):
 
 class _PlanCache:
     """Packed-weights cache shared by the score modules: rebuilt when any parameter is modified
-    (tensor version counters), re-created with a larger capacity when a bigger batch arrives."""
+    (tensor version counters), re-created with a larger capacity when a bigger batch arrives.
+    Writes through ``param.data`` (which carry their own version counter) are invisible to the key: the mirror's
+    ``ExponentialMovingAverage.copy_to / restore`` write through the parameter for that reason, and code that edits
+    ``.data`` by hand calls ``module.invalidate_plan()``."""
 
     def __init__(self):
+        self.plan, self.key = None, None
+
+    def invalidate(self):
+        if self.plan is not None:
+            self.plan.close()
         self.plan, self.key = None, None
 
     def get(self, module, batch, n_joints, hidden, embed, n_blocks):
@@ -113,6 +121,11 @@ class ScoreModelFC_Adv(nn.Module):
         self.cond_joint_mask_prob = config.training.cond_joint_mask_prob
         self._plans = _PlanCache()
         self.gemm_mode = engine.DEFAULT_MODE
+
+    def invalidate_plan(self):
+        """Drop the packed weights; the next forward re-packs them from the current parameters (needed only after
+        in-place edits through ``param.data``, which do not move the parameters' version counters)."""
+        self._plans.invalidate()
 
     def zedo_plan(self, batch):
         """The packed plan for a batch of this size (also used by the fused sampler fast path)."""

@@ -36,18 +36,21 @@ class ExponentialMovingAverage:
         for shadow, param in zip(self.shadow_params, _trainable(parameters)):
             shadow.sub_(weight * (shadow - param))
 
+    @torch.no_grad()
     def copy_to(self, parameters):
-        """Overwrite the trainable parameters with their moving averages."""
+        """Overwrite the trainable parameters with their moving averages.  Written through the parameter itself
+        (not ``param.data``) so its version counter moves and the score modules re-pack their plan."""
         for shadow, param in zip(self.shadow_params, _trainable(parameters)):
-            param.data.copy_(shadow.data)
+            param.copy_(shadow)
 
     def store(self, parameters):
         """Remember the current parameters (to ``restore`` them after an evaluation with the EMA)."""
         self.collected_params = [p.clone() for p in parameters]
 
+    @torch.no_grad()
     def restore(self, parameters):
         for saved, param in zip(self.collected_params, parameters):
-            param.data.copy_(saved.data)
+            param.copy_(saved)
 
     def state_dict(self):
         return {'decay': self.decay, 'num_updates': self.num_updates, 'shadow_params': self.shadow_params}
