@@ -367,6 +367,18 @@ def run_gpu_arm(args):
     h2d = (h_db2d.numel() * 4 + h_K.numel() * 4 + h_cl.numel() * 4 + h_gt.numel() * 8) * world
     d2h = h_out.numel() * 4 + h_err.numel() * 8 + h_idx.numel() * 4 if rank == 0 else 0
     n_prod = {"split3": 3, "fp8lo": 4, "split2": 2, "fp16": 1}.get(args.mode, 0)
+    # the HBM-bound kernels of a step against the measured copy bandwidth: ALGORITHMIC bytes per row of a launch
+    #  over the live CUDA-event time of this run.  first layer: 64-column operand read (256 B) + the output
+    # images a later layer reads (fp8lo: hi16 + hi8 + lo8 + lo16 = 6 B per channel; split3: 4 B); post_dense: hi16 + lo16
+    # of 1024 channels read + 64 float32 written; geometry: SURVEY 8(d)'s 672 B of pose state + eps read (256 B) + the
+    # first layer's operand written (256 B).
+    alg_bytes = {"first_layer": 256 + 1024 * (6 if args.mode == "fp8lo" else 4), "post_dense": 1024 * 4 + 256,
+                 "geometry": 672 + 256 + 256}
+    other_hbm = {}
+    for k, per_row in alg_bytes.items():
+        if k in prof and prof[k][0] > 0 and not control:
+            gbs = per_row * rows / (prof[k][0] / 1e3) / 1e9
+            other_hbm[k] = {"algorithmic_bytes_per_row": per_row, "GBps": gbs, "frac_of_hbm_peak": gbs / peaks["hbm"]}
 
     if rank == 0:
         cpu = None
@@ -399,6 +411,7 @@ def run_gpu_arm(args):
                          "mma_issue_factor": {"split3": 3, "fp8lo": 2, "split2": 2}.get(args.mode, 1),
                          "avg_launch_ms": hid_ms, "launches_timed": hid_n,
                          "other_kernels_ms": {k: v[0] for k, v in prof.items() if k != "hidden_layer"},
+                         "other_kernels_hbm": other_hbm,
                          "other_kernels": {
                              "ipo_fit (K4, 500 Adam iterations in registers)": {
                                  "ms": ipo_ms, "bound": "fp32 ALU (serial per pose)", "poses": B,

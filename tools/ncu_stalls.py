@@ -62,10 +62,14 @@ def main():
             md.append("\nWarps stalled per issued instruction, by reason: " +
                       ", ".join(f"{k} {v:.2f}" for k, v in stalls if v >= 0.05) + "\n")
             def norm(n):
-                return n.replace("zedo::", "").replace("(int)", "").replace("void ", "").replace(" ", "")
+                return (n.replace("zedo::", "").replace("(int)", "").replace("(bool)", "").replace("void ", "")
+                        .replace(" ", ""))
             match = [k for k in kernels if norm(k["name"]) == norm(d["Kernel Name"])]
-            if not match or (li > 0 and len(kernels) < len(raw) - 2):
-                continue  # the source page of a multi-launch report only carries its first launch
+            per = len(kernels) // max(1, len(raw) - 2)  # source blocks per captured launch (ncu 2025: two views each)
+            if per >= 1 and norm(kernels[li * per]["name"]) == norm(d["Kernel Name"]):
+                match = [kernels[li * per]]  # launch order
+            elif not match or li > 0:
+                continue  # a source page that only carries the first launch of a multi-launch report
             k = match[0]
             ix = {n: i for i, n in enumerate(k["hdr"])}
             by_s, by_i = collections.Counter(), collections.Counter()

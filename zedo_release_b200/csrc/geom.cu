@@ -527,7 +527,7 @@ oil_rays_kernel(const float* __restrict__ uv, const float* __restrict__ Kmat, fl
 // above), then -- four threads per pose, thread q owns joints q, q + 4, ... -- the translation solve (SOLVE) and the
 // projection on the precomputed unit rays; x is updated in place and the first GEMM's operand emitted.
 template <bool SOLVE, int NIT>
-__global__ void __launch_bounds__(kRayThreads)
+__global__ void __launch_bounds__(kRayThreads, 4)
 oil_geom_kernel(const float4* __restrict__ rays_a, const float2* __restrict__ rays_b,
                 const double* __restrict__ pose_c, float* x, float* T, __half* __restrict__ xa, int64_t B, int J,
                 const float* __restrict__ eps_prev, float neg_half_beta, float gsq, float std, float dt,
@@ -543,18 +543,40 @@ oil_geom_kernel(const float4* __restrict__ rays_a, const float2* __restrict__ ra
   const int n_it = NIT ? NIT : ray_iters(J);
 
   griddep_wait();  // PDL: x / eps / T come from the previous kernels
-  // stage the poses, one row per warp iteration (coalesced), applying the previous step's predictor update
-#pragma unroll 2
-  for (int r = warp; r < n; r += kWarps) {
-    const float* xg = x + (p0 + r) * D;
-    const float* eg = eps_prev != nullptr ? eps_prev + (p0 + r) * 64 : nullptr;
-    for (int c = lane; c < D; c += 32) {
-      float xv = xg[c];
-      if (eg != nullptr) {
-        xv = em_pf_update(xv, eg[c], neg_half_beta, gsq, std, dt);
-        if (dump != nullptr) dump[(p0 + r) * D + c] = xv;
+  // stage the poses, one row per warp iteration (coalesced), applying the previous step's predictor update.  All
+  // loads of a warp's rows are issued before the first one is consumed: the phase is bound by global-load latency
+  // (r02 ncu: 43 % of the stall samples sat on the first use of eps), not by bandwidth or issue slots.
+  {
+    constexpr int kRows = kRayPoses / kWarps;  // rows per warp
+    const int c1 = lane + 32;                  // D <= 64: at most two columns per lane
+    float xv[kRows][2], ev[kRows][2];
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      const int r = warp + k * kWarps;
+      const float* xg = x + (p0 + r) * D;
+      const float* eg = eps_prev + (p0 + r) * 64;
+      const bool ok = r < n;
+      xv[k][0] = ok && lane < D ? xg[lane] : 0.f;
+      xv[k][1] = ok && c1 < D ? xg[c1] : 0.f;
+      ev[k][0] = ok && eps_prev != nullptr && lane < D ? eg[lane] : 0.f;
+      ev[k][1] = ok && eps_prev != nullptr && c1 < D ? eg[c1] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      const int r = warp + k * kWarps;
+      if (r >= n) break;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = lane + 32 * h;
+        if (c < D) {
+          float v = xv[k][h];
+          if (eps_prev != nullptr) {
+            v = em_pf_update(v, ev[k][h], neg_half_beta, gsq, std, dt);
+            if (dump != nullptr) dump[(p0 + r) * D + c] = v;
+          }
+          xs[r * Dp + c] = v;
+        }
       }
-      xs[r * Dp + c] = xv;
     }
   }
   if (!SOLVE)
