@@ -125,6 +125,31 @@ def test_geometry_kernels_agree_bitwise(zr, monkeypatch, J, B):
             assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("eps_value", [0.0, 1e-30, 3e-10, -2.5e3])
+def test_predictor_update_division_paths_agree_bitwise(zr, eps_value):
+    """The step kernel on precomputed rays divides by the (launch-uniform) marginal std through its correctly rounded
+    reciprocal inside a guarded exponent range and falls back to the IEEE division outside it; the other kernels always
+    divide.  A network whose output is a constant (post_dense.weight = 0) drives both branches: exact zero and 1e-30 take
+    the fall-back, 3e-10 and -2.5e3 the reciprocal path -- the loops must agree bit for bit."""
+    B, J = 200, 17
+    ds = zo.make_synthetic_dataset(B, n_joints=J, seed=9)
+    W = dict(zo.make_weights(seed=0, n_joints=J))
+    W["post_dense.weight"] = np.zeros_like(W["post_dense.weight"])
+    W["post_dense.bias"] = np.full_like(W["post_dense.bias"], eps_value)
+    uv, K, conf = ds["db_2d"][:, :, :2], ds["camera_param"], ds["db_2d"][:, :, 2]
+    plan = zr.ScorePlan(W, n_joints=J, max_batch=B)
+    out = {}
+    for poses in ("warp", "rays"):
+        zr._native.set_option(zr._native.OPT_GEOM_KERNEL, {"warp": 1, "rays": 3}[poses])
+        x, T = dev(ds["db_3d"]), dev(zo.init_translation(uv, K, 3.0).reshape(B, 3))
+        plan.oil_loop(x, T, dev(uv), dev(K), dev(conf), zo.oil_time_grid()[100:108], phase_switch=3, mode="split3")
+        out[poses] = (x, T)
+    plan.close()
+    zr._native.set_option(zr._native.OPT_GEOM_KERNEL, 0)
+    assert torch.isfinite(out["warp"][0]).all()
+    assert torch.equal(out["warp"][0], out["rays"][0]) and torch.equal(out["warp"][1], out["rays"][1])
+
+
 def test_grad_field_empty_batch(zr, geom_kernel):
     e = torch.empty((0, 17, 3), device="cuda")
     g, T = zr.grad_field(torch.empty((0, 17, 2), device="cuda"), e, torch.empty((0, 3, 3), device="cuda"))

@@ -7,7 +7,7 @@ import zedo_oracle as zo
 import zedo_release_b200 as zr
 W = zo.make_weights(seed=0)
 res = {}
-for B in (128, 886, 1024, 2048, 4096, 8192):
+for B in (128, 886, 1024, 2048, 4096, 8192, 16384, 32768):
     ds = zo.make_synthetic_dataset(B, seed=1)
     t = lambda a: torch.tensor(np.ascontiguousarray(a), device="cuda")
     plan = zr.ScorePlan(W, n_joints=17, max_batch=B, device=0)
@@ -21,4 +21,4 @@ for B in (128, 886, 1024, 2048, 4096, 8192):
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
     res[B] = dt * 1e3  # us per step (1000 steps -> ms total == us/step)
     plan.close()
-print(os.environ.get("ZEDO_SMALL_TILES", "default"), json.dumps(res))
+print(os.environ.get("ZEDO_SMALL_TILES", "default"), os.environ.get("ZEDO_GEOM", "auto"), json.dumps(res))

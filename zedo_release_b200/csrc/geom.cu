@@ -35,6 +35,27 @@ __device__ __forceinline__ float em_pf_update(float xv, float e, float neg_half_
   return __fadd_rn(xv, __fmul_rn(drift, dt));
 }
 
+// The same update with the division (-e) / std evaluated through the correctly rounded reciprocal r = RN(1 / std), which
+// is uniform over the launch: q0 = RN(-e r), rem = -e - q0 std (exact in one FMA), q = RN(q0 + rem r).  By Markstein's
+// theorem q is the correctly rounded quotient whenever nothing under- or overflows on the way, so inside the guarded
+// exponent range the result has the bits of __fdiv_rn (checked on 8e7 random pairs); outside it (zeros,
+// denormals, huge values) the IEEE division itself runs.  6 instructions instead of the ~12 of the generic sequence.
+__device__ __noinline__ float fdiv_rn_rare(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float em_pf_update_rcp(float xv, float e, float neg_half_beta, float g2, float std, float rstd,
+                                                  bool std_ok, float dt) {
+  const float ne = -e, ae = fabsf(e);
+  float score;
+  if (std_ok && ae >= 0x1p-60f && ae <= 0x1p60f) {
+    const float q0 = __fmul_rn(ne, rstd);
+    const float rem = __fmaf_rn(-q0, std, ne);
+    score = __fmaf_rn(rem, rstd, q0);
+  } else {
+    score = fdiv_rn_rare(ne, std);  // out of line: keeps the 16 unrolled call sites of the staging loop small
+  }
+  const float drift = __fsub_rn(__fmul_rn(neg_half_beta, xv), __fmul_rn(g2, score));
+  return __fadd_rn(xv, __fmul_rn(drift, dt));
+}
+
 // general 3x3 inverse by the adjugate (skew allowed), every product and sum rounded once
 __device__ __forceinline__ float det2_rn(float a, float b, float c, float d) {
   return __fsub_rn(__fmul_rn(a, d), __fmul_rn(b, c));
@@ -526,13 +547,17 @@ oil_rays_kernel(const float* __restrict__ uv, const float* __restrict__ Kmat, fl
 // One OIL step's geometry for kRayPoses poses per CTA: fused predictor update of the previous step (as in the kernels
 // above), then -- four threads per pose, thread q owns joints q, q + 4, ... -- the translation solve (SOLVE) and the
 // projection on the precomputed unit rays; x is updated in place and the first GEMM's operand emitted.
-template <bool SOLVE, int NIT>
+// JCT = the number of joints as a compile-time constant (17, 12; 0 = read it from the argument): row lengths, strides and
+// trip counts fold, which removes a fifth of the kernel's (issue-bound) instructions.
+template <bool SOLVE, int JCT>
 __global__ void __launch_bounds__(kRayThreads, 4)
 oil_geom_kernel(const float4* __restrict__ rays_a, const float2* __restrict__ rays_b,
-                const double* __restrict__ pose_c, float* x, float* T, __half* __restrict__ xa, int64_t B, int J,
+                const double* __restrict__ pose_c, float* x, float* T, __half* __restrict__ xa, int64_t B, int J_rt,
                 const float* __restrict__ eps_prev, float neg_half_beta, float gsq, float std, float dt,
                 float* __restrict__ dump) {
   extern __shared__ __align__(16) float geom_smem[];
+  constexpr int NIT = JCT ? (JCT + kGeomTpp - 1) / kGeomTpp : 0;
+  const int J = JCT ? JCT : J_rt;
   const int D = 3 * J, Dp = D | 1;
   float* xs = geom_smem;               // [P][Dp]
   float* ts = xs + kRayPoses * Dp;     // [P][3]
@@ -549,6 +574,8 @@ oil_geom_kernel(const float4* __restrict__ rays_a, const float2* __restrict__ ra
   {
     constexpr int kRows = kRayPoses / kWarps;  // rows per warp
     const int c1 = lane + 32;                  // D <= 64: at most two columns per lane
+    const float rstd = __frcp_rn(std);
+    const bool std_ok = fabsf(std) >= 0x1p-60f && fabsf(std) <= 0x1p60f;
     float xv[kRows][2], ev[kRows][2];
 #pragma unroll
     for (int k = 0; k < kRows; ++k) {
@@ -571,7 +598,7 @@ oil_geom_kernel(const float4* __restrict__ rays_a, const float2* __restrict__ ra
         if (c < D) {
           float v = xv[k][h];
           if (eps_prev != nullptr) {
-            v = em_pf_update(v, ev[k][h], neg_half_beta, gsq, std, dt);
+            v = em_pf_update_rcp(v, ev[k][h], neg_half_beta, gsq, std, rstd, std_ok, dt);
             if (dump != nullptr) dump[(p0 + r) * D + c] = v;
           }
           xs[r * Dp + c] = v;
@@ -800,12 +827,12 @@ int launch_oil_rays(const float* uv, const float* K, float* conf, float4* rays_a
   return 0;
 }
 
-template <bool SOLVE, int NIT>
+template <bool SOLVE, int JCT>
 static cudaError_t launch_oil_geom_t(const float4* rays_a, const float2* rays_b, const double* pose_c, float* x,
                                      float* T, __half* xa, int64_t B, int J, cudaStream_t st, const float* eps_prev,
                                      float nhb, float g2, float sd, float dt, float* dump) {
   const size_t smem = (size_t)kRayPoses * (((3 * J) | 1) + 3) * sizeof(float);
-  return launch_pdl(oil_geom_kernel<SOLVE, NIT>, dim3((unsigned)((B + kRayPoses - 1) / kRayPoses)), dim3(kRayThreads),
+  return launch_pdl(oil_geom_kernel<SOLVE, JCT>, dim3((unsigned)((B + kRayPoses - 1) / kRayPoses)), dim3(kRayThreads),
                     smem, st, rays_a, rays_b, pose_c, x, T, xa, B, J, eps_prev, nhb, g2, sd, dt, dump);
 }
 
@@ -823,17 +850,16 @@ int launch_oil_geom(const float4* rays_a, const float2* rays_b, const double* po
   } else {
     eps_prev = nullptr;
   }
-  const int nit = ray_iters(J);
   cudaError_t e;
 #define ZEDO_OIL_GEOM(S, N) \
   e = launch_oil_geom_t<S, N>(rays_a, rays_b, pose_c, x, T, xa, B, J, st, eps_prev, nhb, g2, sd, dt, dump)
   if (solve_T) {
-    if (nit == 5) ZEDO_OIL_GEOM(true, 5);
-    else if (nit == 3) ZEDO_OIL_GEOM(true, 3);
+    if (J == 17) ZEDO_OIL_GEOM(true, 17);
+    else if (J == 12) ZEDO_OIL_GEOM(true, 12);
     else ZEDO_OIL_GEOM(true, 0);
   } else {
-    if (nit == 5) ZEDO_OIL_GEOM(false, 5);
-    else if (nit == 3) ZEDO_OIL_GEOM(false, 3);
+    if (J == 17) ZEDO_OIL_GEOM(false, 17);
+    else if (J == 12) ZEDO_OIL_GEOM(false, 12);
     else ZEDO_OIL_GEOM(false, 0);
   }
 #undef ZEDO_OIL_GEOM
