@@ -78,6 +78,10 @@ def test_mode_constants_match_the_header(built_lib):
         assert defs[f"ZEDO_GEMM_{name.upper()}"] == value
     assert sorted(engine.GEMM_MODES.values()) == sorted(v for k, v in defs.items() if k.startswith("ZEDO_GEMM_"))
     assert defs["ZEDO_NET_SCORE_FC_ADV"] == built_lib.NET_SCORE_FC_ADV and defs["ZEDO_NET_CONTROL"] == built_lib.NET_CONTROL
+    opts = {k[len("ZEDO_"):]: v for k, v in defs.items() if k.startswith("ZEDO_OPT_") and k != "ZEDO_OPT_COUNT"}
+    assert sorted(opts.values()) == list(range(defs["ZEDO_OPT_COUNT"]))
+    for name, value in opts.items():
+        assert getattr(built_lib, name) == value, name
 
 
 def test_options_and_argument_validation(built_lib):
@@ -87,6 +91,10 @@ def test_options_and_argument_validation(built_lib):
     nat.set_option(nat.OPT_GEOM_KERNEL, 2)
     assert nat.get_option(nat.OPT_GEOM_KERNEL) == 2
     nat.set_option(nat.OPT_GEOM_KERNEL, 0)
+    assert nat.get_option(nat.OPT_LEAN_EW) == 16 and nat.get_option(nat.OPT_GRAPH) == 0  # defaults of the r02b options
+    nat.set_option(nat.OPT_GRAPH, 1)
+    assert nat.get_option(nat.OPT_GRAPH) == 1
+    nat.set_option(nat.OPT_GRAPH, 0)
     assert nat.lib.zedo_set_option(99, 1) == -1
     assert nat.lib.zedo_set_option(nat.OPT_EXPERIMENT, 1) == -5  # timing experiments are not in the shipped build
     # negative / absurd element counts are argument errors, not std::length_error through ctypes

@@ -23,6 +23,21 @@ for kind, W in ((nat.NET_SCORE_FC_ADV, zo.make_weights(0)), (nat.NET_CONTROL, zo
 big = zr.ScorePlan(zo.make_weights(0), n_joints=17, max_batch=4096, device=0)  # CTA-pair path (more than 18 row tiles)
 x = t(np.random.default_rng(0).normal(0, 0.3, (4096, 17, 3)).astype(np.float32))
 big.forward(x, 10.0)
+# the loop on precomputed rays (large-batch geometry form) and as one CUDA graph, on a side stream, ragged batch
+ds2 = zo.make_synthetic_dataset(4001, seed=4)
+uv, K, conf = t(ds2["db_2d"][:, :, :2]), t(ds2["camera_param"]), t(ds2["db_2d"][:, :, 2])
+xl, Tl = t(ds2["db_3d"]), t(zo.init_translation(ds2["db_2d"][:, :, :2], ds2["camera_param"], 3.0).reshape(4001, 3))
+nat.set_option(nat.OPT_GEOM_KERNEL, 3)
+big.oil_loop(xl, Tl, uv, K, conf, zo.oil_time_grid()[:6], phase_switch=2, dump_steps=(1, 5))
+side = torch.cuda.Stream()
+torch.cuda.synchronize()
+nat.set_option(nat.OPT_GRAPH, 1)
+with torch.cuda.stream(side):
+    for _ in range(2):
+        big.oil_loop(xl, Tl, uv, K, conf, zo.oil_time_grid()[:6], phase_switch=2)
+    side.synchronize()
+nat.set_option(nat.OPT_GRAPH, 0)
+nat.set_option(nat.OPT_GEOM_KERNEL, 0)
 torch.cuda.synchronize()
 big.close()
 print("sanitize smoke done, finite:", bool(torch.isfinite(res).all()))
