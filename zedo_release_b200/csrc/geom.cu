@@ -5,7 +5,9 @@
 //   optional least-squares translation, rows weighted conf^2, sign flip on T_z < 0   (:73-93)
 //   r^_j = r_j/|r_j|; p_j = X_j + T; g_j = (p_j . r^_j) r^_j - p_j                   (:33-36,99,109)
 // Per pose they move x (r/w), uv, conf, K, T = 672 bytes at J = 17 and (optionally) emit the first GEMM's fp16
-// hi/lo operand in the blocked interleaved layout (common.cuh).  Two kernels, one arithmetic:
+// hi/lo operand in the blocked interleaved layout (common.cuh).  Two general kernels, one arithmetic (a third form,
+// for the OIL loop at large batches, evaluates everything that does not depend on the pose once per loop: see
+// oil_rays_kernel / oil_geom_kernel below):
 //   * grad_field_warp_kernel: one warp per pose, lane j owns joint j (J <= 32) -- lowest latency, small batches;
 //   * grad_field_block_kernel: 128 poses per CTA staged in shared memory by coalesced loads, four threads per
 //     pose (joints q, q+4, ...) -- ~3.5x fewer instructions per pose, used once the batch fills the GPU.
@@ -617,7 +619,7 @@ oil_geom_kernel(const float4* __restrict__ rays_a, const float2* __restrict__ ra
     const int64_t slot0 = (((p0 + pp) >> 3) * n_it) * 32 + (pp & 7) * 4 + q;
     const float4* ra = rays_a + slot0;
     float* xp = xs + pp * Dp;
-    constexpr int kMaxIt = NIT ? NIT : 8;  // J <= 32
+    constexpr int kMaxIt = NIT ? NIT : 6;  // 3 J <= 64 -> J <= 21
     float4 hw[kMaxIt];
 #pragma unroll
     for (int it = 0; it < kMaxIt; ++it)
@@ -840,7 +842,7 @@ int launch_oil_geom(const float4* rays_a, const float2* rays_b, const double* po
                     __half* xa, int64_t B, int J, cudaStream_t st, const float* eps_prev, const SdeCoef* prev,
                     float* dump) {
   if (B == 0) return 0;
-  if (J < 1 || J > 32) return ZEDO_E_SHAPE;
+  if (J < 1 || 3 * J > kBlockK) return ZEDO_E_SHAPE;  // the staging phase holds a row in two columns per lane
   float nhb = 0.f, g2 = 0.f, sd = 1.f, dt = 0.f;
   if (eps_prev != nullptr && prev != nullptr) {
     nhb = -0.5f * prev->beta_t;
