@@ -17,13 +17,30 @@ def align_to_gt(pose, pose_gt):
 
 
 def procrustes(A, B, scaling=True, reflection='best'):
-    """MATLAB-style procrustes(A = target, B = input): returns (d, Z, tform) with Z the transformed
-    B.  Only the configuration ``align_to_gt`` uses (scaling=True, reflection='best') is implemented;
-    ``tform`` is reduced to the entries that follow from Z."""
+    """MATLAB-style procrustes(A = target, B = input): returns (d, Z, tform) with Z the transformed B and
+    ``tform = {'rotation', 'scale', 'translation'}`` such that ``Z = scale * B @ rotation + translation``
+    (transforms.py:42-128).  The configuration ``align_to_gt`` uses (scaling=True, reflection='best') runs in the
+    Procrustes kernel of csrc/eval.cu; ``tform`` is read back from its output (Z is an exact similarity image of B, so
+    the 3x3 map follows from the centred point sets).  Any other configuration is not on the evaluation path: it is
+    served by the reference's own function when a reference checkout is known (``lib.install(reference_root=...)``)
+    and raises ``NotImplementedError`` otherwise."""
     if not scaling or reflection != 'best':
-        raise NotImplementedError("only scaling=True, reflection='best' (the align_to_gt call) is implemented")
+        import sys
+        ref = sys.modules.get(__name__.rpartition(".")[0] + "._reference_transforms")
+        if ref is None and "__getattr__" in globals():
+            globals()["__getattr__"]("image_to_camera_frame")  # loads the reference's transforms.py once
+            ref = sys.modules.get(__name__.rpartition(".")[0] + "._reference_transforms")
+        if ref is None:
+            raise NotImplementedError("only scaling=True, reflection='best' (the align_to_gt call) runs on the device; "
+                                      "other configurations need the reference checkout (lib.install(reference_root=...))")
+        return ref.procrustes(np.array(A, dtype=np.float64), np.array(B, dtype=np.float64), scaling, reflection)
     A = np.asarray(A, dtype=np.float64)
+    B = np.asarray(B, dtype=np.float64)
     Z = align_to_gt(B, A)
     A0 = A - A.mean(0)
     d = float(((A - Z) ** 2).sum() / (A0 ** 2).sum())
-    return d, Z, {'translation': None, 'rotation': None, 'scale': None}
+    B0, Z0 = B - B.mean(0), Z - Z.mean(0)
+    sR = np.linalg.lstsq(B0, Z0, rcond=None)[0]          # scale * rotation (3x3)
+    scale = float(np.sqrt((Z0 ** 2).sum() / (B0 ** 2).sum()))
+    R = sR / scale
+    return d, Z, {'rotation': R, 'scale': scale, 'translation': Z.mean(0) - scale * B.mean(0) @ R}
