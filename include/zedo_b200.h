@@ -47,8 +47,9 @@ extern "C" {
 #define ZEDO_GEMM_FP8LO  4  /* tcgen05, fp16 main product + the two low-order products in e4m3 (kind::f8f6f4):
                                2 fp16-pass equivalents, 2^-15 product error (split3: 2^-22, split2: 2^-12); holds every parity
                                bound of split3 and is what the host layer uses when no mode is named.
-                               A plan with a 1024x1024 weight whose max/rms exceeds 16 (too heavy-tailed for one
-                               e4m3 scale per matrix) runs this mode as SPLIT3; ZEDO_FP8LO_FORCE=1 overrides. */
+                               The e4m3 weight images sit under one power-of-two scale per matrix that keeps four
+                               significant bits down to max / 2^10; a plan with a 1024x1024 weight whose max / median |w|
+                               exceeds 1024 (too heavy-tailed even for that) runs this mode as SPLIT3; ZEDO_FP8LO_FORCE=1 overrides. */
 
 /* network kinds */
 #define ZEDO_NET_SCORE_FC_ADV 0  /* ScoreModelFC_Adv          (model.py:97-298)          */

@@ -53,8 +53,13 @@ class Layer:
         self.w64 = w.astype(np.float64)
         self.hi = fp16(ws)
         self.lo = fp16(ws - self.hi)
-        self.hi8 = e4m3(self.hi * f32(2.0 ** -11))
-        self.lo8 = e4m3(self.lo)
+        # the fp8lo images are packed 2^6 higher (pack_weight_f8: max |w| s in [2^14, 2^15)), which keeps e4m3(W_hi 2^-11)
+        # out of the e4m3 subnormals down to max / 2^10
+        self.s8 = f32(64.0)
+        ws8 = (ws * self.s8).astype(f32)
+        hi_s = fp16(ws8)
+        self.hi8 = e4m3(hi_s * f32(2.0 ** -11))
+        self.lo8 = e4m3(fp16(ws8 - hi_s))
         self.hilo = (self.hi + self.lo).astype(f32)  # exact in float32 (22 bits)
 
     def apply(self, a, mode):
@@ -71,7 +76,7 @@ class Layer:
         if mode == "split3":
             return (a_hi @ self.hi.T + a_lo @ self.hi.T + a_hi @ self.lo.T) / self.s
         if mode == "fp8lo":
-            return (a_hi @ self.hi.T + e4m3(a_lo * f32(2.0 ** 11)) @ self.hi8.T + e4m3(a_hi) @ self.lo8.T) / self.s
+            return (a_hi @ self.hi.T + (e4m3(a_lo * f32(2.0 ** 11)) @ self.hi8.T + e4m3(a_hi) @ self.lo8.T) / self.s8) / self.s
         raise ValueError(mode)
 
 

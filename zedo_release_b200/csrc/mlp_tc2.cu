@@ -283,7 +283,10 @@ static int launch_pair_ew(const LayerArgs& a, int num_sms, cudaStream_t st) {
   if (a.m_tiles % 2 != 0) return ZEDO_E_SHAPE;
   const int pairs = (a.m_tiles / 2) * a.n_tiles;
   if (pairs == 0) return 0;
-  const int max_pairs = num_sms / 2;
+  int max_pairs = num_sms / 2;
+  // experiment (bits 8..15 of the experiment option): run on that many CTA pairs only -- does the layer follow the number
+  // of SMs that ingest (a per-SM bound) or stay put (the chip-wide L2 output cap)?
+  if (ZEDO_EXPERIMENTS && (a.dbg >> 8) > 0 && (a.dbg >> 8) < max_pairs) max_pairs = a.dbg >> 8;
   const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
   ZEDO_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(tc_threads(EW)), Cfg::kSmemBytes, st, a));
   ZEDO_LAUNCH_CHECK();
