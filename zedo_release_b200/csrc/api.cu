@@ -96,7 +96,7 @@ static float pow2_scale_for(const float* w, int64_t n) {
 }
 
 static int pack_weight(const float* w, int N, int K, int bn, PackedWeight* out) {
-  const int n_pad = (int)round_up(N, bn), k_pad = (int)round_up(K, kBlockK);
+  const int n_pad = (int)round_up(N, bn), k_pad = (int)round_up(K, kXaCols);
   const float s = pow2_scale_for(w, (int64_t)N * K);
   std::vector<__half> buf((size_t)n_pad * k_pad * 2, __float2half_rn(0.f));
   for (int n = 0; n < N; ++n) {
@@ -132,7 +132,7 @@ static int pack_weight(const float* w, int N, int K, int bn, PackedWeight* out) 
 // of Gaussian weights; r02c).  lo8 = e4m3(lo16) has its maximum at 16; the float32 accumulator has 2^90 of headroom.
 constexpr float kF8WeightShift = 64.f;
 static int pack_weight_f8(const float* w, int N, int K, int rows, PackedWeight* out) {
-  const int n_pad = (int)round_up(N, rows), k_pad = (int)round_up(K, kBlockK);
+  const int n_pad = (int)round_up(N, rows), k_pad = (int)round_up(K, kXaCols);
   const int num_kb = k_pad / kBlockK;
   const float s = pow2_scale_for(w, (int64_t)N * K) * kF8WeightShift;
   const size_t blk_bytes = (size_t)rows * kBlockK * 4;  // 32 KiB for 128 rows
@@ -521,7 +521,7 @@ int net_forward(zedo_plan* p, const float* x, const float* tbl, int64_t B, int m
     a.o_fmt = f8 ? 1 : 0;
     a.o_flags = op.out_flags;
     {
-      ProfScope ps(p, op.epi == EPI_LINEAR_F32 ? 2 : (a.num_kb == 1 ? 0 : 1), st);
+      ProfScope ps(p, op.epi == EPI_LINEAR_F32 ? 2 : (w.k_pad == kXaCols ? 0 : 1), st);
       const PackedWeight& wp = p->packed_pair[op.weight];
       const PackedWeight& w64 = p->packed64[op.weight];
       const PackedWeight& w8 = p->packed_f8[op.weight];
@@ -887,7 +887,7 @@ static int plan_create_impl(zedo_plan** out, const zedo_net_desc* desc, int32_t 
     PLAN_TRY(upload(p, &p->freqs, fr.data(), fr.size()));
   }
   // workspaces
-  PLAN_TRY(dev_alloc(p, &p->xa, (size_t)p->m_pad * kBlockK * 2));
+  PLAN_TRY(dev_alloc(p, &p->xa, (size_t)p->m_pad * kXaCols * 2));
   for (int i = 0; i < p->n_act; ++i) {
     __half* a = nullptr;
     PLAN_TRY(dev_alloc(p, &a, (size_t)p->m_pad * H * 3));  // room for format-1 blocks (48 KiB per 128 x 64)

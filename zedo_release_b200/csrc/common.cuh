@@ -74,7 +74,12 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 //   * one linear bulk copy (cp.async.bulk) of the tile image is directly consumable by tcgen05.mma;
 //   * an epilogue warp (lane = row) writes 32 consecutive rows of one chunk = 512 contiguous bytes
 //     per store instruction (4 L1 wavefronts instead of 32 for a row-major or 128B-swizzled image).
-constexpr int kBlockK = 64;        // halves per tile row (128 bytes)
+#ifndef ZEDO_BLOCK_K
+#define ZEDO_BLOCK_K 64
+#endif
+constexpr int kBlockK = ZEDO_BLOCK_K;  // columns (K) per block: 64, or 32 in the -DZEDO_BLOCK_K=32 layout study (r02c)
+constexpr int kXaCols = 64;        // width of the first layer's operand x (3J <= 64) and K padding of every weight
+static_assert(kBlockK == 64 || kBlockK == 32, "block width");
 constexpr int kActTileRows = 128;  // BLOCK_M
 
 __host__ __device__ inline int64_t blocked_half_offset(int64_t row, int64_t col, int64_t cols_padded,

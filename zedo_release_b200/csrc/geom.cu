@@ -188,7 +188,7 @@ grad_field_warp_kernel(const float* __restrict__ uv, const float* x, const float
                        float* T, int solve_T, int clamp_inplace, float* g_out, float* x_out,
                        __half* __restrict__ xa, int64_t B, int J, const float* __restrict__ eps_prev,
                        float neg_half_beta, float gsq, float std, float dt, float* __restrict__ dump) {
-  __shared__ float stage[kGeomWarps][kBlockK];
+  __shared__ float stage[kGeomWarps][kXaCols];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int64_t pose = (int64_t)blockIdx.x * kGeomWarps + wib;
@@ -293,8 +293,8 @@ grad_field_warp_kernel(const float* __restrict__ uv, const float* x, const float
         hi[e] = pack_half2(h0, h1);
         lo[e] = pack_half2(l0, l1);
       }
-      const int64_t oh = blocked_half_offset(pose, lane * 8, kBlockK, kActTileRows, 0);
-      const int64_t ol = blocked_half_offset(pose, lane * 8, kBlockK, kActTileRows, 1);
+      const int64_t oh = blocked_half_offset(pose, lane * 8, kXaCols, kActTileRows, 0);
+      const int64_t ol = blocked_half_offset(pose, lane * 8, kXaCols, kActTileRows, 1);
       *reinterpret_cast<uint4*>(xa + oh) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       *reinterpret_cast<uint4*>(xa + ol) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
@@ -444,7 +444,7 @@ grad_field_block_kernel(const float* __restrict__ uv, const float* x, const floa
   if (xa != nullptr) {
     // rows p0 .. p0 + n of the first GEMM's A operand: 64 halves per row (3J padded with zeros), hi and lo;
     // consecutive threads write consecutive 16-byte chunks of the blocked layout
-    for (int item = tid; item < kGeomPoses * (kBlockK / 8); item += kGeomThreads) {
+    for (int item = tid; item < kGeomPoses * (kXaCols / 8); item += kGeomThreads) {
       const int r = item & (kGeomPoses - 1), ch = item / kGeomPoses;
       if (r >= n) continue;
       const float* xp = xs + r * Dp;
@@ -460,9 +460,9 @@ grad_field_block_kernel(const float* __restrict__ uv, const float* x, const floa
         hi[e] = pack_half2(h0, h1);
         lo[e] = pack_half2(l0, l1);
       }
-      *reinterpret_cast<uint4*>(xa + blocked_half_offset(p0 + r, ch * 8, kBlockK, kActTileRows, 0)) =
+      *reinterpret_cast<uint4*>(xa + blocked_half_offset(p0 + r, ch * 8, kXaCols, kActTileRows, 0)) =
           make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(xa + blocked_half_offset(p0 + r, ch * 8, kBlockK, kActTileRows, 1)) =
+      *reinterpret_cast<uint4*>(xa + blocked_half_offset(p0 + r, ch * 8, kXaCols, kActTileRows, 1)) =
           make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
   }
@@ -699,7 +699,7 @@ oil_geom_kernel(const float4* __restrict__ rays_a, const float2* __restrict__ ra
   if (xa != nullptr) {
     // rows p0 .. p0 + n of the first GEMM's A operand: 64 halves per row (3J padded with zeros), hi and lo;
     // consecutive threads write consecutive 16-byte chunks of the blocked layout
-    for (int item = tid; item < kRayPoses * (kBlockK / 8); item += kRayThreads) {
+    for (int item = tid; item < kRayPoses * (kXaCols / 8); item += kRayThreads) {
       const int r = item & (kRayPoses - 1), ch = item / kRayPoses;
       if (r >= n) continue;
       const float* xp = xs + r * Dp;
@@ -715,9 +715,9 @@ oil_geom_kernel(const float4* __restrict__ rays_a, const float2* __restrict__ ra
         hi[e] = pack_half2(h0, h1);
         lo[e] = pack_half2(l0, l1);
       }
-      *reinterpret_cast<uint4*>(xa + blocked_half_offset(p0 + r, ch * 8, kBlockK, kActTileRows, 0)) =
+      *reinterpret_cast<uint4*>(xa + blocked_half_offset(p0 + r, ch * 8, kXaCols, kActTileRows, 0)) =
           make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(xa + blocked_half_offset(p0 + r, ch * 8, kBlockK, kActTileRows, 1)) =
+      *reinterpret_cast<uint4*>(xa + blocked_half_offset(p0 + r, ch * 8, kXaCols, kActTileRows, 1)) =
           make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
   }
@@ -742,9 +742,9 @@ __global__ void pack_x_kernel(const float* __restrict__ x, __half* __restrict__ 
     hi[e] = pack_half2(h0, h1);
     lo[e] = pack_half2(l0, l1);
   }
-  *reinterpret_cast<uint4*>(xa + blocked_half_offset(row, chunk * 8, kBlockK, kActTileRows, 0)) =
+  *reinterpret_cast<uint4*>(xa + blocked_half_offset(row, chunk * 8, kXaCols, kActTileRows, 0)) =
       make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<uint4*>(xa + blocked_half_offset(row, chunk * 8, kBlockK, kActTileRows, 1)) =
+  *reinterpret_cast<uint4*>(xa + blocked_half_offset(row, chunk * 8, kXaCols, kActTileRows, 1)) =
       make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
@@ -842,7 +842,7 @@ int launch_oil_geom(const float4* rays_a, const float2* rays_b, const double* po
                     __half* xa, int64_t B, int J, cudaStream_t st, const float* eps_prev, const SdeCoef* prev,
                     float* dump) {
   if (B == 0) return 0;
-  if (J < 1 || 3 * J > kBlockK) return ZEDO_E_SHAPE;  // the staging phase holds a row in two columns per lane
+  if (J < 1 || 3 * J > kXaCols) return ZEDO_E_SHAPE;  // the staging phase holds a row in two columns per lane
   float nhb = 0.f, g2 = 0.f, sd = 1.f, dt = 0.f;
   if (eps_prev != nullptr && prev != nullptr) {
     nhb = -0.5f * prev->beta_t;

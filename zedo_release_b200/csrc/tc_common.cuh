@@ -238,7 +238,7 @@ __device__ __forceinline__ void epilogue_tile(const LayerArgs& args, uint32_t tm
     const int col0 = nt * BN + g * 32;
     // position of this thread's 32 columns inside the blocked [M_pad, N_pad] activation layout
     const int kbo = col0 / kBlockK;
-    const int hsel = (col0 / 32) & 1;
+    const int hsel = (col0 % kBlockK) / 32;  // which 32-column half of a 64-wide block (0 for 32-wide blocks)
     // chunk c of this row lives at c * (128 rows * 8 halves) + r * 8 inside the (mt, kbo) hi image
     const int64_t row_off = ((int64_t)mt * nkb_out + kbo) * kBlk + (int64_t)r * 8;
     constexpr int kChunkStride = kActTileRows * 8;
