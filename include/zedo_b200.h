@@ -103,7 +103,10 @@ int zedo_plan_reserve(zedo_plan* plan, int32_t max_steps, int32_t gemm_mode, voi
                                       capturing ~7 launches per step costs about a third of a small-batch loop, so it pays
                                       for callers that replay a loop on persistent buffers; calls on the legacy default
                                       stream (which cannot be captured) are launched directly (ZEDO_GRAPH) */
-#define ZEDO_OPT_COUNT           8
+#define ZEDO_OPT_TMA_2SM         8  /* CTA-pair kernel: operand stages by tensor-map TMA whose completion is credited to the leader
+                                      CTA's barrier (cp.async.bulk.tensor ... cta_group::2) instead of linear bulk copies plus a
+                                      relay hop from the peer CTA; same bytes, same results; default 1 (ZEDO_TMA_2SM) */
+#define ZEDO_OPT_COUNT           9
 int zedo_set_option(int32_t option, int32_t value);
 int zedo_get_option(int32_t option, int32_t* value);
 

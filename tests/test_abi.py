@@ -95,6 +95,7 @@ def test_options_and_argument_validation(built_lib):
     nat.set_option(nat.OPT_GRAPH, 1)
     assert nat.get_option(nat.OPT_GRAPH) == 1
     nat.set_option(nat.OPT_GRAPH, 0)
+    assert nat.get_option(nat.OPT_TMA_2SM) == 1  # r02c: tensor-map stage copies of the CTA-pair kernel are the default
     assert nat.lib.zedo_set_option(99, 1) == -1
     assert nat.lib.zedo_set_option(nat.OPT_EXPERIMENT, 1) == -5  # timing experiments are not in the shipped build
     # negative / absurd element counts are argument errors, not std::length_error through ctypes

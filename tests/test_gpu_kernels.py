@@ -220,6 +220,30 @@ def test_fp8lo_with_heavy_tailed_weights(zr, plan17):
     assert torch.equal(a, b) and rel_err(a.cpu().numpy(), ref) < 2e-5
 
 
+@pytest.mark.parametrize("mode", ["fp8lo", "split3"])
+def test_pair_kernel_stage_copies_tensor_map_vs_linear(zr, mode):
+    """The CTA-pair kernel fills its stages either with tensor-map TMA completing on the leader CTA's barrier
+    (cp.async.bulk.tensor ... cta_group::2, the default) or with linear bulk copies plus a relay arrive from the peer CTA
+    (ZEDO_OPT_TMA_2SM = 0): the same bytes reach the same MMAs, so the network output is bit-identical -- on a ragged
+    batch that takes the pair kernel (> 18 row tiles, odd tile count, partial last tile)."""
+    nat = zr._native
+    B = 19 * 128 + 77
+    W = zo.make_weights(seed=0)
+    x = dev(np.random.default_rng(9).normal(0, 0.4, (B, 17, 3)).astype(np.float32))
+    plan = zr.ScorePlan(W, n_joints=17, max_batch=B, device=0)
+    out = {}
+    try:
+        for v in (1, 0, 1):
+            nat.set_option(nat.OPT_TMA_2SM, v)
+            out.setdefault(v, []).append(plan.forward(x, 49.95, mode=mode).clone())
+    finally:
+        nat.set_option(nat.OPT_TMA_2SM, 1)
+        plan.close()
+    assert torch.equal(out[1][0], out[0][0]) and torch.equal(out[1][0], out[1][1])
+    ref = zo.score_forward(W, x[:256].cpu().numpy(), np.float32(49.95))
+    assert rel_err(out[1][0][:256].cpu().numpy(), ref) < 4e-5
+
+
 @pytest.mark.parametrize("B", [1, 127, 128, 129, 300, 4096])
 def test_score_forward_vs_oracle_ragged_batches(zr, plan17, B):
     W = zo.make_weights(seed=0)

@@ -18,7 +18,7 @@ GEMM_SPLIT3, GEMM_FP16, GEMM_FP32, GEMM_SPLIT2, GEMM_FP8LO = 0, 1, 2, 3, 4
 NET_SCORE_FC_ADV, NET_CONTROL = 0, 1
 PRED_EULER_MARUYAMA, PRED_REVERSE_DIFFUSION = 0, 1
 UPD_ANCESTRAL_VP, UPD_ANCESTRAL_VE, UPD_LANGEVIN, UPD_ALD = 0, 1, 2, 3
-OPT_GEOM_KERNEL, OPT_PDL, OPT_SMALL_TILES, OPT_CTA_PAIRS, OPT_FP8LO_FORCE, OPT_EXPERIMENT, OPT_LEAN_EW, OPT_GRAPH = range(8)
+OPT_GEOM_KERNEL, OPT_PDL, OPT_SMALL_TILES, OPT_CTA_PAIRS, OPT_FP8LO_FORCE, OPT_EXPERIMENT, OPT_LEAN_EW, OPT_GRAPH, OPT_TMA_2SM = range(9)
 
 #: every symbol ``include/zedo_b200.h`` declares (checked by tests/test_abi.py)
 EXPORTS = (

@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>
 #include <cuda_fp8.h>
 
 #include "kernels.cuh"
@@ -24,9 +25,9 @@ struct Options {
   std::atomic<int> v[ZEDO_OPT_COUNT];
   Options() {
     const int defaults[ZEDO_OPT_COUNT] = {/*GEOM_KERNEL*/ 0, /*PDL*/ 1, /*SMALL_TILES*/ 18, /*CTA_PAIRS*/ 1,
-                                          /*FP8LO_FORCE*/ 0, /*EXPERIMENT*/ 0, /*LEAN_EW*/ 16, /*GRAPH*/ 0};
+                                          /*FP8LO_FORCE*/ 0, /*EXPERIMENT*/ 0, /*LEAN_EW*/ 16, /*GRAPH*/ 0, /*TMA_2SM*/ 1};
     const char* env[ZEDO_OPT_COUNT] = {"ZEDO_GEOM", "ZEDO_PDL", "ZEDO_SMALL_TILES", "ZEDO_TC2", "ZEDO_FP8LO_FORCE",
-                                       "ZEDO_DBG", "ZEDO_LEAN_EW", "ZEDO_GRAPH"};
+                                       "ZEDO_DBG", "ZEDO_LEAN_EW", "ZEDO_GRAPH", "ZEDO_TMA_2SM"};
     for (int i = 0; i < ZEDO_OPT_COUNT; ++i) {
       int val = defaults[i];
       if (const char* e = getenv(env[i])) {  // read once, here; never on a launch path
@@ -84,6 +85,7 @@ struct PackedWeight {
   __half* dev = nullptr;  // blocked hi/lo [N_pad, K_pad]
   float descale = 1.f;
   int n_pad = 0, k_pad = 0, bn = 0;
+  int tmap = -1;  // index into plan->tmaps_dev (CTA-pair tiles only)
 };
 
 static float pow2_scale_for(const float* w, int64_t n) {
@@ -93,6 +95,35 @@ static float pow2_scale_for(const float* w, int64_t n) {
   int e;
   std::frexp(mx, &e);  // mx = f * 2^e, f in [0.5, 1)  ->  mx * 2^(9-e) in [256, 512)
   return std::ldexp(1.f, 9 - e);
+}
+
+// ---- tensor maps (driver entry point through the runtime: no -lcuda) -----------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+// a device buffer seen as a dense byte matrix [bytes / 128][128]; one box = 256 rows = 32 KiB lands in shared memory
+// exactly as a linear bulk copy of those bytes would
+static int make_linear_tmap(CUtensorMap* m, void* base, size_t bytes) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr || bytes % 128 != 0 || bytes < 32768) return ZEDO_E_STATE;
+  const cuuint64_t gdim[2] = {128, (cuuint64_t)(bytes / 128)};
+  const cuuint64_t gstride[1] = {128};
+  const cuuint32_t box[2] = {128, 256};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : ZEDO_E_STATE;
 }
 
 static int pack_weight(const float* w, int N, int K, int bn, PackedWeight* out) {
@@ -238,6 +269,8 @@ struct zedo_plan {
   std::vector<float*> wz2, bz2, gam2c, bet2c;  // per block: zc_b{k}_2 weight/bias, b{k}_gnorm2_copy affine
   std::vector<float*> static_rows;             // per table row: NULL or a [H] vector broadcast over the steps
   float* zeros_h = nullptr;
+  // tensor maps of the CTA-pair kernel's operands (byte matrices [bytes / 128][128], 32 KiB box): act[i] -> i, then weights
+  CUtensorMap* tmaps_dev = nullptr;
   std::vector<void*> owned;
   // ZEDO_OPT_GRAPH: the last zedo_oil_loop call captured as one CUDA graph, replayed while the call repeats verbatim
   struct LoopGraph {
@@ -499,6 +532,7 @@ int net_forward(zedo_plan* p, const float* x, const float* tbl, int64_t B, int m
   if (f8 && !p->use_pairs) return ZEDO_E_INVALID;
   const int nprod = (mode == ZEDO_GEMM_SPLIT3 || mode == ZEDO_GEMM_FP8LO) ? 3 : (mode == ZEDO_GEMM_SPLIT2 ? 2 : 1);
   if (!xa_ready && (rc = launch_pack_x(x, p->xa, B, p->D, st))) return rc;
+  const bool tma2sm = p->tmaps_dev != nullptr && option_get(ZEDO_OPT_TMA_2SM) != 0;
   for (const GemmOp& op : p->program) {
     const PackedWeight& w = p->packed[op.weight];
     LayerArgs a{};
@@ -536,6 +570,10 @@ int net_forward(zedo_plan* p, const float* x, const float* tbl, int64_t B, int m
           a.W = w8.dev;
           a.descale = w8.descale;
           a.m_tiles = (m_tiles + 1) & ~1;
+          if (tma2sm && w8.tmap >= 0 && op.in_buf >= 0) {
+            a.tmapA = p->tmaps_dev + op.in_buf;
+            a.tmapW = p->tmaps_dev + w8.tmap;
+          }
           rc = launch_layer_tc2(a, 4, op.epi, p->num_sms, st);
         }
       } else if (m_tiles <= p->small_batch_tiles && w64.dev != nullptr && op.epi != EPI_LINEAR_F32) {
@@ -545,6 +583,10 @@ int net_forward(zedo_plan* p, const float* x, const float* tbl, int64_t B, int m
       } else if (p->use_pairs && wp.dev != nullptr && op.epi != EPI_LINEAR_F32) {
         a.W = wp.dev;                        // CTA-pair kernel: 256 poses x 256 channels per cluster
         a.m_tiles = (m_tiles + 1) & ~1;      // activation buffers are padded to 256 rows
+        if (tma2sm && wp.tmap >= 0 && op.in_buf >= 0 && nprod == 3) {
+          a.tmapA = p->tmaps_dev + op.in_buf;
+          a.tmapW = p->tmaps_dev + wp.tmap;
+        }
         rc = launch_layer_tc2(a, nprod, op.epi, p->num_sms, st);
       } else {
         rc = launch_layer_tc(a, w.bn, nprod, op.epi, p->num_sms, st);
@@ -899,6 +941,29 @@ static int plan_create_impl(zedo_plan** out, const zedo_net_desc* desc, int32_t 
   PLAN_TRY(dev_alloc(p, &p->rays_a, oil_rays_slots(p->m_pad, desc->n_joints)));
   PLAN_TRY(dev_alloc(p, &p->rays_b, oil_rays_slots(p->m_pad, desc->n_joints)));
   PLAN_TRY(dev_alloc(p, &p->pose_c, (size_t)p->m_pad * 4));
+  {
+    // tensor maps: activation buffers first, then the CTA-pair weight tiles (split3 and fp8lo packings)
+    std::vector<CUtensorMap> maps;
+    bool ok = true;
+    auto add_map = [&](void* base, size_t bytes) -> int {
+      CUtensorMap m;
+      if (!ok || make_linear_tmap(&m, base, bytes) != 0) {
+        ok = false;
+        return -1;
+      }
+      maps.push_back(m);
+      return (int)maps.size() - 1;
+    };
+    for (int i = 0; i < p->n_act; ++i) add_map(p->act[i], (size_t)p->m_pad * H * 3 * sizeof(__half));
+    for (PackedWeight& w : p->packed_pair)
+      if (w.dev != nullptr) w.tmap = add_map(w.dev, (size_t)w.n_pad * w.k_pad * 4);
+    for (PackedWeight& w : p->packed_f8)
+      if (w.dev != nullptr) w.tmap = add_map(w.dev, (size_t)w.n_pad * w.k_pad * 4);
+    if (ok && !maps.empty()) {
+      PLAN_TRY(dev_alloc(p, &p->tmaps_dev, maps.size()));
+      PLAN_TRY((int)cudaMemcpy(p->tmaps_dev, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    }  // else: tmaps_dev stays NULL and the pair kernel keeps its linear bulk copies
+  }
   PLAN_TRY(ensure_tables(p, 1, (cudaStream_t)0));
   PLAN_TRY((int)cudaDeviceSynchronize());
 #undef NEED

@@ -21,6 +21,11 @@ struct LayerArgs {
   int dbg;  // timing experiments only (env ZEDO_DBG): 1 = no bulk copies after the first fill, 2 = no MMAs
   int a_fmt;  // block format of A (common.cuh): 0 = [hi16 | lo16], 1 = [hi16 | hi8 | lo8 | lo16]
   int o_fmt;  // block format of out / resid / addend
+  // CTA-pair kernel, optional: tensor maps (device pointers to CUtensorMap, 64-byte aligned) that describe the A buffer
+  // and the W tiles as [bytes / 128][128] byte matrices with a 32 KiB box; with them both CTAs' stage copies complete on the
+  // LEADER's barrier (cp.async.bulk.tensor ... cta_group::2) and the peer's relay hop disappears.  NULL = linear bulk copies.
+  const void* tmapA;
+  const void* tmapW;
   int o_flags;  // format-1 output: bit 0 = some consumer reads the e4m3 images (hi8, lo8), bit 1 = some consumer reads
                 // lo16 (residual / addend epilogue, post_dense); images nobody reads are neither formed nor stored
 };

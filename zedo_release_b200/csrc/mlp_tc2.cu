@@ -20,6 +20,22 @@
 
 namespace zedo {
 
+// Stage-event trace of CTA pair 0 (experiments build, experiment bit 16): clock64 of this SM at the hand-offs of the
+// operand pipeline, for stage iterations [kTraceSkip, kTraceSkip + kTraceLen) of the launch.  Events: 0 producer starts
+// waiting for the stage to be free, 1 it is free, 2 copies issued, 3 MMA / relay lane sees the stage full, 4 leader sees
+// the peer's stage full, 5 MMAs + commit issued (peer: relay arrive sent).  Read back with zedo_debug_stage_trace.
+#if ZEDO_EXPERIMENTS
+constexpr int kTraceLen = 512, kTraceSkip = 96, kTraceEvents = 6;
+__device__ unsigned long long g_stage_trace[2][kTraceEvents][kTraceLen];
+#define ZEDO_TRACE(ev, it)                                                                                  \
+  do {                                                                                                      \
+    if ((args.dbg & 16) && blockIdx.x < 2 && (it) >= kTraceSkip && (it) < kTraceSkip + kTraceLen)            \
+      g_stage_trace[blockIdx.x][ev][(it) - kTraceSkip] = (unsigned long long)clock64();                      \
+  } while (0)
+#else
+#define ZEDO_TRACE(ev, it) do { } while (0)
+#endif
+
 __device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                               uint32_t accumulate) {
   asm volatile(
@@ -123,6 +139,9 @@ layer_tc2_kernel(const LayerArgs args) {
   griddep_launch_dependents();
 
   const int num_kb = args.num_kb;
+  // tensor-map copies completing on the leader's barrier need 32 KiB operand stages (NPROD 3 / 4 with 64-column blocks)
+  const bool tma2 = Cfg::kABytes == 32768 && Cfg::kBBytes == 32768 && args.tmapA != nullptr && args.tmapW != nullptr &&
+                    !(ZEDO_EXPERIMENTS && (args.dbg & 5));
   const int num_pairs = (args.m_tiles / 2) * args.n_tiles;  // m_tiles is even (plan pads to 256 rows)
   const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
 
@@ -131,6 +150,7 @@ layer_tc2_kernel(const LayerArgs args) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int sit = 0;  // stage iteration of this launch (trace index)
       for (int pt = pair0; pt < num_pairs; pt += pair_stride) {
         const int mp = pt / args.n_tiles, nt = pt - mp * args.n_tiles;
         const int mt = 2 * mp + (int)rank;
@@ -138,8 +158,10 @@ layer_tc2_kernel(const LayerArgs args) {
         const int64_t a_blk = act_block_halves(args.a_fmt);
         const __half* a_src = args.A + ((int64_t)mt * num_kb) * a_blk;
         const __half* w_src = args.W + ((int64_t)(2 * nt + (int)rank) * num_kb) * 2 * (Cfg::kHalfN * kBlockK);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb; ++kb, ++sit) {
+          ZEDO_TRACE(0, sit);
           mbar_wait(&empty[stage], phase ^ 1);
+          ZEDO_TRACE(1, sit);
           if (ZEDO_EXPERIMENTS && (args.dbg & 1) && (pt != pair0 || kb >= S)) {
             mbar_arrive(&full[stage]);  // experiment: MMA on stale tiles, no L2 -> SMEM traffic
             if (++stage == S) {
@@ -161,10 +183,22 @@ layer_tc2_kernel(const LayerArgs args) {
             }
             continue;
           }
-          mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-          bulk_g2s(sA + stage * Cfg::kABytes, a_src + (int64_t)kb * a_blk, Cfg::kABytes, &full[stage]);
-          bulk_g2s(sB + stage * Cfg::kBBytes, w_src + (int64_t)kb * 2 * (Cfg::kHalfN * kBlockK), Cfg::kBBytes,
-                   &full[stage]);
+          if (tma2) {
+            // both CTAs' copies are credited to the LEADER's full[stage]: one wait for the MMA lane, no relay hop.
+            // A box = 256 rows of 128 bytes = 32 KiB; a block of A is a_blk * 2 bytes, a W half tile 32 KiB.
+            const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+            if (leader) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+            tma2d_g2s_2cta(sA + stage * Cfg::kABytes, args.tmapA, 0,
+                           (int)((((int64_t)mt * num_kb + kb) * a_blk * 2) >> 7), lead_full);
+            tma2d_g2s_2cta(sB + stage * Cfg::kBBytes, args.tmapW, 0,
+                           (int)((((int64_t)(2 * nt + (int)rank) * num_kb + kb) * Cfg::kBBytes) >> 7), lead_full);
+          } else {
+            mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+            bulk_g2s(sA + stage * Cfg::kABytes, a_src + (int64_t)kb * a_blk, Cfg::kABytes, &full[stage]);
+            bulk_g2s(sB + stage * Cfg::kBBytes, w_src + (int64_t)kb * 2 * (Cfg::kHalfN * kBlockK), Cfg::kBBytes,
+                     &full[stage]);
+          }
+          ZEDO_TRACE(2, sit);
           if (++stage == S) {
             stage = 0;
             phase ^= 1;
@@ -176,6 +210,7 @@ layer_tc2_kernel(const LayerArgs args) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int sit = 0;
       if (leader) {
         // ===================== MMA issuer (leader CTA only) =====================
         constexpr uint32_t idesc = make_idesc_f16(256, BN);
@@ -186,9 +221,13 @@ layer_tc2_kernel(const LayerArgs args) {
           mbar_wait(&tmem_empty[as], aphase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-          for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(&full[stage], phase);
-            mbar_wait(&peer_full[stage], phase);
+          for (int kb = 0; kb < num_kb; ++kb, ++sit) {
+            if (ZEDO_EXPERIMENTS && (args.dbg & 64)) mbar_wait_spin(&full[stage], phase); else mbar_wait(&full[stage], phase);
+            ZEDO_TRACE(3, sit);
+            if (!tma2) {
+              if (ZEDO_EXPERIMENTS && (args.dbg & 64)) mbar_wait_spin(&peer_full[stage], phase); else mbar_wait(&peer_full[stage], phase);
+            }
+            ZEDO_TRACE(4, sit);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(sA + stage * Cfg::kABytes);
             const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
@@ -224,6 +263,7 @@ layer_tc2_kernel(const LayerArgs args) {
                 umma_f16_2cta(d_tmem, a_hi + kAStep * k, b_lo + kBStep * k, idesc, 1);
             }
             umma_commit_2cta(&empty[stage]);
+            ZEDO_TRACE(5, sit);
             if (++stage == S) {
               stage = 0;
               phase ^= 1;
@@ -233,10 +273,13 @@ layer_tc2_kernel(const LayerArgs args) {
         }
       } else {
         // ===================== relay (peer CTA): tell the leader this CTA's stage has landed =====================
-        for (int pt = pair0; pt < num_pairs; pt += pair_stride) {
-          for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(&full[stage], phase);
+        // (not needed with tensor-map copies: they complete on the leader's barrier themselves)
+        for (int pt = pair0; pt < num_pairs && !tma2; pt += pair_stride) {
+          for (int kb = 0; kb < num_kb; ++kb, ++sit) {
+            if (ZEDO_EXPERIMENTS && (args.dbg & 64)) mbar_wait_spin(&full[stage], phase); else mbar_wait(&full[stage], phase);
+            ZEDO_TRACE(3, sit);
             mbar_arrive_cluster(&peer_full[stage], 0);
+            ZEDO_TRACE(5, sit);
             if (++stage == S) {
               stage = 0;
               phase ^= 1;
@@ -319,3 +362,11 @@ int launch_layer_tc2(const LayerArgs& a_in, int nprod, int epi, int num_sms, cud
 }
 
 }  // namespace zedo
+
+#if ZEDO_EXPERIMENTS
+// experiments build only: the stage-event trace of the last traced launch, [2 CTAs][6 events][512 iterations] clocks
+extern "C" int zedo_debug_stage_trace(unsigned long long* host, int n) {
+  if (host == nullptr || n != 2 * zedo::kTraceEvents * zedo::kTraceLen) return -1;
+  return (int)cudaMemcpyFromSymbol(host, zedo::g_stage_trace, sizeof(unsigned long long) * (size_t)n);
+}
+#endif

@@ -43,6 +43,41 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// polling wait without the suspend-time hint (experiments: lowest wake-up latency for a single lane on the critical path)
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  int spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((++spins & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+// shared::cluster address of `local` (a shared::cta address of this CTA) in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(cta));
+  return r;
+}
+
+// 2-D tiled TMA load of one box into THIS CTA's shared memory whose completion bytes are credited to a barrier of either
+// CTA of the pair (mbar_cluster = shared::cluster address): what lets both CTAs' operand copies complete on the leader's
+// barrier, the counterpart of CUTLASS' SM100_TMA_2SM_LOAD_2D
+__device__ __forceinline__ void tma2d_g2s_2cta(void* smem_dst, const void* tmap, int c0, int c1, uint32_t mbar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(mbar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
