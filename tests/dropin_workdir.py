@@ -47,6 +47,44 @@ def make_workdir(path, n_poses=64, hypo=2, ipo=10, oil=100, seed=1234):
     return dict(config=cfg, ckpt_dir=os.path.join(path, "ckpt"), ckpt_name="checkpoint_1500.pth", ds=ds)
 
 
+PW3D_CONFIG_TEMPLATE = CONFIG_TEMPLATE.replace("concat_pose_optimization_h36m", "concat_pose_optimization_pw3d")
+
+
+def make_workdir_pw3d(path, n_poses=48, hypo=2, ipo=10, oil=100, seed=4321):
+    """The same for ``run/inference.py`` with the shipped 3DPW config: ``data/3dpw/pw3d_test.npz`` in the file format
+    lib/dataset/pw3d.py:184-199 reads, ``clusters/h36m_cluster{S}.npy`` (run/inference.py:64-65), checkpoint, config."""
+    import torch
+    from zedo_release_b200 import synthetic as sy
+    ds = sy.make_synthetic_dataset(n_poses, seed=seed, n_clusters=hypo)
+    os.makedirs(os.path.join(path, "data", "3dpw"), exist_ok=True)
+    os.makedirs(os.path.join(path, "clusters"), exist_ok=True)
+    os.makedirs(os.path.join(path, "ckpt"), exist_ok=True)
+    np.savez(os.path.join(path, "data", "3dpw", "pw3d_test.npz"), **sy.pw3d_npz_from_arrays(ds))
+    np.save(os.path.join(path, "clusters", f"h36m_cluster{hypo}.npy"), ds["clusters"].astype(np.float32))
+    W = sy.make_weights(seed=0)
+    sd = {"module." + k: torch.tensor(v) for k, v in W.items()}
+    sd["module.sigmas"] = torch.tensor(np.exp(np.linspace(np.log(50), np.log(0.01), 1000)))
+    shadow = [torch.tensor(v) for k, v in W.items()]
+    torch.save({"model_state_dict": sd, "ema": {"decay": 0.9999, "num_updates": 7, "shadow_params": shadow},
+                "step": 1500}, os.path.join(path, "ckpt", "checkpoint_1500.pth"))
+    cfg = os.path.join(path, "zedo_test_config_pw3d.py")
+    with open(cfg, "w") as f:
+        f.write(PW3D_CONFIG_TEMPLATE.format(batch=n_poses, ipo=ipo, oil=oil))
+    return dict(config=cfg, ckpt_dir=os.path.join(path, "ckpt"), ckpt_name="checkpoint_1500.pth", ds=ds)
+
+
+def parse_means(stdout):
+    """The 'mean MPJPE : x' / 'mean PA-MPJPE : x' lines PW3D.eval_multi prints (lib/dataset/pw3d.py:338-341)."""
+    out = {}
+    for line in stdout.splitlines():
+        line = line.strip()
+        if line.startswith("mean MPJPE :"):
+            out["p1"] = float(line.split(":")[1])
+        elif line.startswith("mean PA-MPJPE :"):
+            out["p2"] = float(line.split(":")[1])
+    return out
+
+
 def parse_table(stdout):
     """The 'p1' / 'p2' rows run/opt_main.py prints through eval_multi(print_verbose=True): -> {'p1': [...], 'p2': [...]}."""
     out = {}

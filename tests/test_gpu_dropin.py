@@ -16,7 +16,7 @@ import numpy as np
 import pytest
 
 from conftest import ROOT
-from dropin_workdir import make_workdir, parse_table
+from dropin_workdir import make_workdir, make_workdir_pw3d, parse_means, parse_table
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
@@ -81,3 +81,31 @@ def test_detected_2d_and_gt_flag(workdir):
     t_ref, t_mir = parse_table(out_ref), parse_table(out_mir)
     for proto in ("p1", "p2"):
         assert np.abs(np.array(t_ref[proto]) - np.array(t_mir[proto])).max() <= 1e-4
+
+
+def test_unmodified_inference_driver_3dpw_format(built_lib, tmp_path_factory):
+    """``run/inference.py`` (the in-the-wild driver, north_star: "run/opt_main.py and run/inference.py drive it
+    unchanged") executed as a file with the shipped 3DPW config on a synthetic ``data/3dpw/pw3d_test.npz``: the
+    reference's own ``lib``, then the same file over the mirror.  ``PW3D`` (the reference's loader, its own
+    ``eval_multi``) is taken from the checkout both times; sampler, score network, ``gradient_field_gen`` and ``RotOpt``
+    are the sm_100a kernels the second time.  The printed MPJPE / PA-MPJPE and the saved ``results.npy`` must agree."""
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device: there is no CPU fallback")
+    if not os.path.isfile(os.path.join(REF, "run", "inference.py")):
+        pytest.fail("oracle/_ref is not staged: run `python oracle/fetch_ref.py` in the build container before gpurun")
+    path = str(tmp_path_factory.mktemp("zedo_workdir_pw3d"))
+    w = make_workdir_pw3d(path, n_poses=48, hypo=2, ipo=10, oil=100)
+    args = _driver_args(w) + ["--eval", "--gt"]
+    out_ref = _run([sys.executable, os.path.join(REF, "run", "inference.py")] + args, path, [REF, SHIMS])
+    res_ref = np.load(os.path.join(path, "results.npy"))
+    os.remove(os.path.join(path, "results.npy"))
+    out_mir = _run([sys.executable, "-m", "zedo_release_b200.dropin", REF, "run/inference.py"] + args, path, [ROOT, SHIMS])
+    res_mir = np.load(os.path.join(path, "results.npy"))
+    m_ref, m_mir = parse_means(out_ref), parse_means(out_mir)
+    assert set(m_ref) == {"p1", "p2"} and set(m_mir) == {"p1", "p2"}, (out_ref[-2000:], out_mir[-2000:])
+    assert res_ref.shape == res_mir.shape == (48, 2, 17, 3) and np.isfinite(res_mir).all()
+    for proto in ("p1", "p2"):
+        assert m_ref[proto] > 0.01 and abs(m_ref[proto] - m_mir[proto]) <= 1e-4, (proto, m_ref, m_mir)  # 0.1 mm
+    # per-pose agreement of the saved hypotheses (metres): 10 Adam iterations + 100 OIL steps stay far from chaos
+    assert np.abs(res_ref - res_mir).max() < 2e-3 and np.abs(res_ref - res_mir).mean() < 1e-4
+    print("reference:", m_ref, "mirror:", m_mir, "max |d results|:", float(np.abs(res_ref - res_mir).max()))
