@@ -16,7 +16,7 @@ import numpy as np
 import pytest
 
 from conftest import ROOT
-from dropin_workdir import make_workdir, make_workdir_pw3d, parse_means, parse_table
+from dropin_workdir import make_workdir, make_workdir_3dhp, make_workdir_pw3d, parse_3dhp, parse_means, parse_table
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
@@ -109,3 +109,28 @@ def test_unmodified_inference_driver_3dpw_format(built_lib, tmp_path_factory):
     # per-pose agreement of the saved hypotheses (metres): 10 Adam iterations + 100 OIL steps stay far from chaos
     assert np.abs(res_ref - res_mir).max() < 2e-3 and np.abs(res_ref - res_mir).mean() < 1e-4
     print("reference:", m_ref, "mirror:", m_mir, "max |d results|:", float(np.abs(res_ref - res_mir).max()))
+
+
+def test_unmodified_driver_3dhp_format_pck_auc(built_lib, tmp_path_factory):
+    """``run/opt_main.py`` with the shipped MPI-INF-3DHP config on a synthetic ``data/3dhp/mpii3d_test.pkl``: the
+    reference's ``MPII3DHP`` loader and its ``eval_multi`` (PCK, AUC, hypothesis std, per-action table;
+    lib/dataset/mpii3dHP.py:424-511) come from the checkout both times; over the mirror its ``compute_PCK`` /
+    ``compute_AUC`` / ``align_to_gt`` imports resolve to the device kernels (zedo_pck_counts, the Procrustes kernel)."""
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device: there is no CPU fallback")
+    path = str(tmp_path_factory.mktemp("zedo_workdir_3dhp"))
+    w = make_workdir_3dhp(path, n_poses=56, hypo=2, ipo=10, oil=100)
+    args = _driver_args(w) + ["--gt"]
+    driver = os.path.join(REF, "run", "opt_main.py")
+    out_ref = _run([sys.executable, driver] + args, path, [REF, SHIMS])
+    out_mir = _run([sys.executable, "-m", "zedo_release_b200.dropin", REF, "run/opt_main.py"] + args, path, [ROOT, SHIMS])
+    r_ref, r_mir = parse_3dhp(out_ref), parse_3dhp(out_mir)
+    assert set(r_ref) == {"p1", "p2"} and set(r_mir) == {"p1", "p2"}, (out_ref[-3000:], out_mir[-3000:])
+    for proto in ("p1", "p2"):
+        a, b = r_ref[proto], r_mir[proto]
+        assert np.isfinite(a["row"]).all() and a["row"][-1] > 0.01
+        assert np.abs(np.array(a["row"]) - np.array(b["row"])).max() <= 1e-4          # 0.1 mm, per action and average
+        # 56 x 17 joints: one joint crossing a 5 mm threshold moves PCK by 0.105 and AUC by 0.0034 per cent
+        assert abs(a["pck"] - b["pck"]) <= 0.22 and abs(a["auc"] - b["auc"]) <= 0.05, (a, b)
+        assert np.abs(np.array(a["std"]) - np.array(b["std"])).max() <= 1e-4
+    print("reference:", r_ref, "\nmirror:   ", r_mir)

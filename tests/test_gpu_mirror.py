@@ -255,6 +255,25 @@ def test_procrustes_returns_the_reference_tform(lib, golden):
         assert tf1["scale"] == 1 and np.abs(np.sqrt((B0 ** 2).sum()) - np.sqrt(((Z1 - Z1.mean(0)) ** 2).sum())) < 1e-9
 
 
+def test_compute_pck_auc_have_the_reference_signature(lib, golden):
+    """``lib.algorithms.advanced.utils.compute_PCK / compute_AUC`` (utils.py:814-849, imported by the reference's
+    MPII3DHP loader) on the device: equal to the reference's formula -- strict ``<`` on errors in millimetres, all joints
+    or ``eval_joints``, AUC = mean over linspace(0, 150, 31)."""
+    from lib.algorithms.advanced.utils import compute_AUC, compute_PCK
+    g = golden("eval")
+    gts = (g["gts"] - g["gts"][:, 0:1]).astype(np.float64)
+    preds = g["preds"][:, 1].astype(np.float32)
+    err_mm = np.sqrt(((preds.astype(np.float64) - gts) ** 2).sum(-1)) * 1000.0   # [N, J]
+    for joints in (None, [1, 2, 3, 14, 15, 16]):
+        e = err_mm if joints is None else err_mm[:, joints]
+        want = [100.0 * float((e < t).sum()) / e.size for t in np.linspace(0, 150, 31)]
+        assert abs(compute_PCK(gts, preds, eval_joints=joints) - want[30]) < 1e-9
+        assert abs(compute_PCK(gts, preds, eval_joints=joints, threshold=50) - want[10]) < 1e-9
+        assert abs(compute_AUC(gts, preds, eval_joints=joints) - float(np.mean(want))) < 1e-9
+    with pytest.raises(NotImplementedError):
+        compute_PCK(gts, preds, threshold=42)
+
+
 def test_dataset_eval_variants(lib, golden):
     """valid_ind filtering, the literal sample_interval semantics and the 3DHP extras (PCK / AUC / std)."""
     from lib.dataset.synthetic import ArrayPoseDataset

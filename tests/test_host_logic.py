@@ -212,14 +212,14 @@ def test_mirror_falls_through_to_the_reference_checkout(built_lib):
         "from lib.algorithms.advanced import losses, sampling, sde_lib\n"
         "from lib.algorithms.advanced.simple_zeroshot_opt import gradient_field_gen, RotOpt\n"
         "from lib.utils.transforms import image_to_camera_frame, align_to_gt\n"
-        "from lib.algorithms.advanced.utils import compute_PCK, get_score_fn\n"
+        "from lib.algorithms.advanced.utils import compute_PCK, get_score_fn, mean_cov\n"
         "import os\n"
         "f = lambda o: os.path.abspath(o.__code__.co_filename if hasattr(o, '__code__') else o.__file__)\n"
         f"ref, mir = {ref!r}, {os.path.join(ROOT, 'zedo_release_b200')!r}\n"
         "assert f(H36MDataset3D.__init__).startswith(ref) and f(generic).startswith(ref) and f(losses).startswith(ref)\n"
-        "assert f(image_to_camera_frame).startswith(ref) and f(compute_PCK).startswith(ref)\n"
+        "assert f(image_to_camera_frame).startswith(ref) and f(mean_cov).startswith(ref)\n"
         "assert f(sampling).startswith(mir) and f(sde_lib).startswith(mir) and f(align_to_gt).startswith(mir)\n"
-        "assert f(gradient_field_gen).startswith(mir) and f(get_score_fn).startswith(mir)\n"
+        "assert f(gradient_field_gen).startswith(mir) and f(get_score_fn).startswith(mir) and f(compute_PCK).startswith(mir)\n"
         "print('ok')\n")
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0 and p.stdout.strip().endswith("ok"), p.stderr[-2000:]

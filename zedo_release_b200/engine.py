@@ -317,10 +317,11 @@ def eval_multi(pred: torch.Tensor, gt: torch.Tensor, protocol2: bool = False,
 
 
 @_device_scoped
-def pck_auc(pred: torch.Tensor, gt: torch.Tensor, select: Optional[torch.Tensor] = None,
-            joint_subset: Optional[Sequence[int]] = None) -> Tuple[float, float]:
-    """(PCK@150mm, AUC) of MPI-INF-3DHP (utils.py:814-849) for the hypothesis ``select[n]`` of every pose
-    (the argmin returned by ``eval_multi``; None = hypothesis 0).  pred [N,S,J,3] f32, gt [N,J,3]."""
+def pck_curve(pred: torch.Tensor, gt: torch.Tensor, select: Optional[torch.Tensor] = None,
+              joint_subset: Optional[Sequence[int]] = None) -> np.ndarray:
+    """PCK (per cent) of MPI-INF-3DHP (utils.py:814-849) at the 31 thresholds linspace(0, 150, 31) mm for the hypothesis
+    ``select[n]`` of every pose (the argmin returned by ``eval_multi``; None = hypothesis 0).  pred [N,S,J,3] f32,
+    gt [N,J,3]; returns float64 [31]."""
     pred = _f32(pred, "pred")
     gt = gt.contiguous().double()
     N, S, J = pred.shape[0], pred.shape[1], pred.shape[2]
@@ -331,7 +332,13 @@ def pck_auc(pred: torch.Tensor, gt: torch.Tensor, select: Optional[torch.Tensor]
     nat.check(nat.lib.zedo_pck_counts(_ptr(pred), _ptr(gt), _ptr(select), N, S, J, sub,
                                       len(sub) if sub is not None else 0, _ptr(counts), _stream()), "zedo_pck_counts")
     total = N * (len(sub) if sub is not None else J)
-    pcks = 100.0 * counts.cpu().numpy().astype(np.float64) / max(total, 1)
+    return 100.0 * counts.cpu().numpy().astype(np.float64) / max(total, 1)
+
+
+def pck_auc(pred: torch.Tensor, gt: torch.Tensor, select: Optional[torch.Tensor] = None,
+            joint_subset: Optional[Sequence[int]] = None) -> Tuple[float, float]:
+    """(PCK@150mm, AUC) of MPI-INF-3DHP (utils.py:814-849); see ``pck_curve``."""
+    pcks = pck_curve(pred, gt, select, joint_subset)
     return float(pcks[30]), float(pcks.mean())
 
 

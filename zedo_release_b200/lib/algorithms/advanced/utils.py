@@ -83,3 +83,27 @@ def to_flattened_numpy(x):
 
 def from_flattened_numpy(x, shape):
     return torch.from_numpy(x.reshape(shape))
+
+
+def _pck_percentages(gts, preds, eval_joints):
+    """PCK (per cent) at the 31 thresholds linspace(0, 150, 31) mm, counted by ``zedo_pck_counts`` (csrc/eval.cu)."""
+    from zedo_release_b200 import engine
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.as_tensor(np.ascontiguousarray(np.asarray(gts, dtype=np.float64)), device=dev)
+    p = torch.as_tensor(np.ascontiguousarray(np.asarray(preds, dtype=np.float32)), device=dev)[:, None]
+    return engine.pck_curve(p, g, joint_subset=None if eval_joints is None else [int(j) for j in eval_joints])
+
+
+def compute_PCK(gts, preds, scales=1000, eval_joints=None, threshold=150):
+    """MPI-INF-3DHP PCK with the reference's signature (utils.py:814-836; ``scales`` is ignored there too: the error is
+    always taken in millimetres): per cent of the joints whose error is strictly below ``threshold`` mm.  gts / preds
+    [N, J, 3] in metres.  Thresholds on the 5 mm grid of the AUC (0, 5, ..., 150) are counted on the device."""
+    k = float(threshold) / 5.0
+    if not (0 <= k <= 30 and k == int(k)):
+        raise NotImplementedError("compute_PCK: thresholds on the 0, 5, ..., 150 mm grid of compute_AUC are served")
+    return float(_pck_percentages(gts, preds, eval_joints)[int(k)])
+
+
+def compute_AUC(gts, preds, scales=1000, eval_joints=None):
+    """Mean of the PCK over thresholds linspace(0, 150, 31) mm (utils.py:839-849, mimicking mpii_compute_3d_pck.m)."""
+    return float(np.mean(_pck_percentages(gts, preds, eval_joints)))
