@@ -8,9 +8,14 @@
 // leader's TMEM, rows 128-255 in the peer's, so each CTA's epilogue warps drain their own TMEM exactly
 // as in mlp_tc.cu.
 //
-// Cross-CTA signalling (non-tensor bulk copies cannot signal a peer mbarrier, so the peer relays):
-//   full[s]       own bulk copies landed (per CTA)
-//   peer_full[s]  leader only: the peer's relay lane observed its full[s] and arrived remotely
+// Stage copies and cross-CTA signalling.  Default (r02c, LayerArgs::tmapA / tmapW set): the operand buffers are described
+// to the TMA unit as byte matrices [bytes / 128][128] with a 32 KiB box, and both CTAs issue
+// cp.async.bulk.tensor.2d ... cta_group::2 copies into their OWN shared memory whose completion bytes are credited to the
+// LEADER's full[s]; the leader expects 2 x 64 KiB per stage and its MMA lane waits once.  Fall-back / A-B form
+// (ZEDO_OPT_TMA_2SM = 0, or no cuTensorMapEncodeTiled in the driver): linear cp.async.bulk copies, which can only complete
+// on a barrier of the destination CTA, so the peer relays (this hand-off cost 11 % of the layer, profiles/r02c_tma2sm.md).
+//   full[s]       leader: both CTAs' tensor-map copies landed | linear form: own bulk copies landed (per CTA)
+//   peer_full[s]  linear form, leader only: the peer's relay lane observed its full[s] and arrived remotely
 //   empty[s]      tcgen05.commit multicast (mask 0b11): the MMAs that read stage s in BOTH CTAs retired
 //   tmem_full[a]  tcgen05.commit multicast: accumulator a complete in both TMEMs
 //   tmem_empty[a] leader only, count 2*EW: one arrive per epilogue warp of both CTAs (peer: remote)
