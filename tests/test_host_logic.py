@@ -223,3 +223,47 @@ def test_mirror_falls_through_to_the_reference_checkout(built_lib):
         "print('ok')\n")
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0 and p.stdout.strip().endswith("ok"), p.stderr[-2000:]
+
+
+def test_reference_loaders_read_the_synthetic_working_directories(built_lib, tmp_path):
+    """The working directories tests/dropin_workdir.py writes for the drop-in driver tests are read here by the
+    reference's OWN loaders (lib/dataset/pw3d.py:184-227, mpii3dHP.py:255-300, h36m.py) from oracle/_ref, on the CPU: the
+    arrays they build are the synthetic dataset's (3D in metres, 2D = projection, K), i.e. the files have the reference's
+    formats.  Subprocess: the reference's `lib` is imported as a top-level package."""
+    import subprocess
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref, "lib")):
+        pytest.skip("oracle/_ref not staged (python oracle/fetch_ref.py needs /root/reference)")
+    code = (
+        "import sys, os, warnings; warnings.simplefilter('ignore')\n"
+        f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})\n"
+        f"sys.path.insert(0, {ref!r}); sys.path.append({os.path.join(ROOT, 'oracle', 'shims')!r})\n"
+        "import numpy as np\n"
+        "from pathlib import Path\n"
+        "from dropin_workdir import make_workdir, make_workdir_pw3d, make_workdir_3dhp\n"
+        f"base = {str(tmp_path)!r}\n"
+        "for name, mk in (('h36m', make_workdir), ('pw3d', make_workdir_pw3d), ('3dhp', make_workdir_3dhp)):\n"
+        "    d = os.path.join(base, name); os.makedirs(d)\n"
+        "    w = mk(d, n_poses=21, hypo=2, ipo=2, oil=5); ds = w['ds']; os.chdir(d)\n"
+        "    if name == 'h36m':\n"
+        "        from lib.dataset.h36m import H36MDataset3D\n"
+        "        t = H36MDataset3D(Path('data', 'h36m'), 'test', gt2d=True, abs_coord=True, sample_interval=1, flip=False)\n"
+        "    elif name == 'pw3d':\n"
+        "        from lib.dataset.pw3d import PW3D\n"
+        "        t = PW3D(Path('data', '3dpw'), 'test', gt2d=True, abs_coord=True, sample_interval=1, flip=False)\n"
+        "    else:\n"
+        "        from lib.dataset.mpii3dHP import MPII3DHP\n"
+        "        t = MPII3DHP(Path('data', '3dhp'), 'test', gt2d=True, abs_coord=True, sample_interval=1, flip=False)\n"
+        "    db3, db2, K = np.asarray(t.db_3d), np.asarray(t.db_2d), np.asarray(t.camera_param)\n"
+        "    assert db3.shape == (21, 17, 3) and db2.shape[:2] == (21, 17) and K.shape == (21, 3, 3), (name, db3.shape, db2.shape)\n"
+        "    want3 = ds['db_3d'] + ds['root'][:, None, :]\n"
+        "    assert np.abs(db3 - want3).max() < 1e-3, (name, np.abs(db3 - want3).max())        # metres, camera frame\n"
+        "    proj = np.einsum('nij,nkj->nki', ds['camera_param'].astype(np.float64), want3.astype(np.float64))\n"
+        "    want2 = proj[:, :, :2] / proj[:, :, 2:3] if name == 'pw3d' else ds['db_2d'][:, :, :2]   # PW3D re-projects its 3D\n"
+        "    assert np.abs(db2[:, :, :2] - want2).max() < 2e-2, (name, np.abs(db2[:, :, :2] - want2).max())   # pixels\n"
+        "    assert np.abs(K - ds['camera_param']).max() < 1e-3, name\n"
+        "    cl = np.load(os.path.join(d, 'clusters', ('3dhp' if name == '3dhp' else 'h36m') + '_cluster2.npy'))\n"
+        "    assert cl.shape == (2, 17, 3) and cl.dtype == np.float32\n"
+        "print('ok')\n")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and p.stdout.strip().endswith("ok"), (p.stdout[-1500:], p.stderr[-2500:])
